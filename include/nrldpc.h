@@ -1,0 +1,181 @@
+/* libnrldpc -- C-ABI of the B200-native (sm_100a) 5G NR LDPC hot path.
+ *
+ * Drop-in boundary for the channel-coding path of InterDigitalInc/NeoRadium v0.4.0 (neoradium/ldpc.py +
+ * neoradium/chancodebase.py).  The reference is pure Python/NumPy and has no FFI of its own; the boundary is the
+ * method surface of LdpcEncoder / LdpcDecoder / ChanCodeBase.  Each entry point below names the reference method
+ * (file:line, relative to the reference root) it replaces.  neoradium_b200/ldpc.py binds these through ctypes and
+ * mirrors the reference classes; INTEGRATION.md shows the stub a NeoRadium maintainer would add.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer in the current CUDA context of `device` (e.g. torch tensor.data_ptr());
+ *     buffers are caller-owned, nothing is retained after the call is enqueued
+ *   - bits are one int8 per bit (0/1), exactly the reference's array layout; LLRs are positive => bit 0
+ *   - `stream` is a cudaStream_t (NULL = default stream); calls are asynchronous unless stated otherwise
+ *   - return value: NRLDPC_OK or an error code; nrldpc_last_error() gives the message (thread local).  No exception
+ *     crosses the ABI.  There is NO CPU fallback: without a usable GPU every compute call fails with NRLDPC_ERR_CUDA.
+ *   - one handle per (device, stream); a handle is not thread-safe, distinct handles are independent
+ */
+#ifndef NRLDPC_H
+#define NRLDPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRLDPC_VERSION 100
+
+typedef struct nrldpc_handle nrldpc_handle;
+typedef void* nrldpc_stream; /* cudaStream_t */
+
+enum {
+    NRLDPC_OK = 0,
+    NRLDPC_ERR_ARG = 1,    /* the reference raises ValueError / AssertionError for these */
+    NRLDPC_ERR_CUDA = 2,   /* CUDA runtime error, no device, launch failure */
+    NRLDPC_ERR_NOMEM = 3
+};
+
+/* generator polynomials of chancodebase.py:37-44 */
+enum { NRLDPC_CRC6 = 0, NRLDPC_CRC11 = 1, NRLDPC_CRC16 = 2, NRLDPC_CRC24A = 3, NRLDPC_CRC24B = 4, NRLDPC_CRC24C = 5 };
+
+/* element types of LLR / belief buffers */
+enum { NRLDPC_F32 = 0, NRLDPC_F64 = 1 };
+
+/* decoder flags */
+enum {
+    NRLDPC_DEC_EARLY_STOP = 1,  /* extension: stop a code block once all parity checks hold after a full iteration */
+    NRLDPC_DEC_ALL_ROWS = 2     /* disable the (exact) skipping of extension rows whose parity LLRs are all zero */
+};
+
+int nrldpc_version(void);
+const char* nrldpc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-only table queries (usable without a GPU)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* LdpcBase.baseGraph, ldpc.py:775-789.  out[P*n] int16 row-major, -1 = no edge, else V % zc (the table keeps the
+ * reference's verbatim 880 entry, ldpc.py:143).  set_index < 0 => derived from zc. */
+int nrldpc_base_graph(int bg, int set_index, int zc, int16_t* out);
+/* liftingSizeSets lookup, ldpc.py:657-666; returns iLS or -1 */
+int nrldpc_lifting_set_index(int zc);
+/* (P, n, k, number of base-graph edges) of ldpc.py:780 */
+int nrldpc_graph_info(int bg, int* rows, int* cols, int* sys_cols, int* edges);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Handle
+ * ---------------------------------------------------------------------------------------------------------------- */
+int nrldpc_create(int device, nrldpc_handle** out);
+int nrldpc_destroy(nrldpc_handle* h);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CRC -- ChanCodeBase.getCrc / checkCrc / appendCrc, chancodebase.py:83-128, 132-157, 161-189
+ * bits: [num_streams, len] int8 with row pitch `stride` (elements).  MSB-first long division, zero initial state.
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* crc_bits [num_streams, c] int8 (may be NULL); rem [num_streams] uint32 remainder, MSB of the CRC in bit c-1 (may
+ * be NULL) */
+int nrldpc_crc(nrldpc_handle* h, const int8_t* bits, int64_t num_streams, int64_t len, int64_t stride, int poly,
+               int8_t* crc_bits, uint32_t* rem, nrldpc_stream stream);
+/* out [num_streams, len + c]: the input followed by its CRC */
+int nrldpc_crc_attach(nrldpc_handle* h, const int8_t* bits, int64_t num_streams, int64_t len, int64_t stride,
+                      int poly, int8_t* out, nrldpc_stream stream);
+/* ok [num_streams] uint8: 1 where the remainder of the whole stream (data || crc) is zero */
+int nrldpc_crc_check(nrldpc_handle* h, const int8_t* bits, int64_t num_streams, int64_t len, int64_t stride,
+                     int poly, uint8_t* ok, nrldpc_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Transport-block configuration shared by the TX and RX chains.  All fields are what LdpcBase.initialize
+ * (ldpc.py:859-892), getRateMatchedCbLens (:846-856) and rateMatch/recoverRate (:1135-1145, :1365-1395) derive;
+ * the host side (neoradium_b200/params.py) computes them with the reference's integer arithmetic.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct nrldpc_tb_config {
+    int32_t bg;   /* base graph 1 | 2 */
+    int32_t zc;   /* lifting size Zc */
+    int32_t K;    /* code block size 22 Zc | 10 Zc */
+    int32_t F;    /* filler bits per code block */
+    int32_t C;    /* code blocks per transport block */
+    int32_t qm;   /* bits per modulation symbol */
+    int32_t nl;   /* transmission layers */
+    int32_t ncb;  /* circular buffer length INCLUDING fillers: N or min(N, nRef) */
+    int32_t rv;   /* redundancy version 0..3 */
+    int32_t reserved;
+    int64_t G;    /* rate-matched bits per transport block the E_r split is derived from (sum E_r >= G) */
+} nrldpc_tb_config;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * TX chain
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* LdpcEncoder.doSegmentation, ldpc.py:1011-1030.  tb [num_tb, B] (pitch tb_stride) already carries its CRC24A.
+ * out [num_tb*C, K]: zero pad at the end of the TB, CRC24B per code block when C > 1, F zero filler bits. */
+int nrldpc_segment(nrldpc_handle* h, const nrldpc_tb_config* cfg, const int8_t* tb, int64_t num_tb, int64_t B,
+                   int64_t tb_stride, int8_t* code_blocks, nrldpc_stream stream);
+
+/* LdpcEncoder.encode, ldpc.py:1057-1090.  code_blocks [num_cb, K] -> coded [num_cb, N] (puncture != 0, the first
+ * 2 Zc bits dropped) or [num_cb, N + 2 Zc]. */
+int nrldpc_encode(nrldpc_handle* h, int bg, int zc, const int8_t* code_blocks, int64_t num_cb, int8_t* coded,
+                  int puncture, nrldpc_stream stream);
+
+/* LdpcEncoder.rateMatch, ldpc.py:1128-1159.  coded [num_tb*C, N] -> out [num_tb, sumE] (pitch out_stride):
+ * bit selection from the filler-less circular buffer starting at k0(rv), then the bit interleaver. */
+int nrldpc_rate_match(nrldpc_handle* h, const nrldpc_tb_config* cfg, const int8_t* coded, int64_t num_tb,
+                      int8_t* out, int64_t out_stride, nrldpc_stream stream);
+
+/* LdpcBase.isValidCodedBlock done right (all rows; the reference's ldpc.py:841-843 returns after the first row).
+ * coded_full [num_cb, n*Zc] un-punctured bits; ok [num_cb] uint8. */
+int nrldpc_parity_check(nrldpc_handle* h, int bg, int zc, const int8_t* coded_full, int64_t num_cb, uint8_t* ok,
+                        nrldpc_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * RX chain
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* LdpcDecoder.recoverRate, ldpc.py:1365-1418.  llr [num_tb, llr_len] (pitch llr_stride; llr_len <= sumE, the tail is
+ * zero-extended as ldpc.py:1402-1403 does) of element type `dtype`; soft_buffer NULL or [num_tb*C, ncb-F] in/out
+ * (HARQ decBuffer: combined into, ldpc.py:1407-1412); out [num_tb*C, ncb] with F entries of 1e20 inserted after the
+ * systematic part (:1415-1418).  All buffers share `dtype`; accumulation order = ascending stream position. */
+int nrldpc_rate_recover(nrldpc_handle* h, const nrldpc_tb_config* cfg, int dtype, const void* llr, int64_t num_tb,
+                        int64_t llr_len, int64_t llr_stride, void* soft_buffer, void* out, nrldpc_stream stream);
+
+/* LdpcDecoder.decode, ldpc.py:1535-1581: layered normalised min-sum (alpha = 0.75), `num_iter` full iterations.
+ *   llr      [num_cb, in_cols*Zc] of in_dtype (pitch llr_stride); in_cols is normally n-2 (66 | 50)
+ *   compute_dtype  NRLDPC_F64 reproduces the reference's float64 arithmetic bit for bit; NRLDPC_F32 is the same
+ *                  operation order evaluated in float32 (no FMA contraction)
+ *   out_cols 22|10 (onlyInfoBits) ... n; bits [num_cb, out_cols*Zc] int8 (or NULL); beliefs same shape in
+ *            compute_dtype (or NULL)
+ *   iters    NULL or [num_cb] int32: iterations actually run (== num_iter unless NRLDPC_DEC_EARLY_STOP) */
+int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr,
+                  int64_t num_cb, int64_t llr_stride, int in_cols, int num_iter, int flags, int out_cols,
+                  int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
+
+/* Fused RX chain: recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A'), i.e. HarqCW.decodeLLRs
+ * (harq.py:165-173) / the documented usage ldpc.py:1234-1251, in ONE kernel per code-block group: rate recovery is
+ * the decoder's load phase, the CRC runs on the decoder's hard decisions in shared memory.
+ *   llr        [num_tb, llr_len] in_dtype, pitch llr_stride
+ *   soft_buffer NULL or [num_tb*C, ncb-F] compute_dtype in/out
+ *   tb_bits    [num_tb, C*per_cb] int8: merged transport block incl. its CRC24A (per_cb = K-F-24 if C>1 else K-F)
+ *   cb_crc_ok  [num_tb*C] uint8 (CRC24B per code block; CRC24A when C == 1) ; tb_crc_ok [num_tb] uint8 (CRC24A
+ *              over the merged block); iters [num_tb*C] int32.  Any output may be NULL. */
+int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,
+                     const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride, void* soft_buffer,
+                     int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok,
+                     uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream);
+
+/* LdpcDecoder.checkCrcAndMerge, ldpc.py:1610-1619, for already decoded blocks.  decoded [num_tb*C, K] ->
+ * tb_bits [num_tb, C*per_cb] and cb_crc_ok [num_tb*C]. */
+int nrldpc_check_crc_and_merge(nrldpc_handle* h, const nrldpc_tb_config* cfg, const int8_t* decoded, int64_t num_tb,
+                               int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok, nrldpc_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Link-level counters (the quantities harq.py:173 / the BLER notebooks accumulate on the host).
+ * counters int64[8] += {code blocks, CB CRC failures, transport blocks, TB CRC failures, bit errors vs ref_bits,
+ * sum of iterations, 0, 0}; reduce across GPUs with one NCCL all-reduce (neoradium_b200/dist.py).
+ * ---------------------------------------------------------------------------------------------------------------- */
+int nrldpc_accumulate_counters(nrldpc_handle* h, int64_t num_tb, int C, const uint8_t* cb_crc_ok,
+                               const uint8_t* tb_crc_ok, const int32_t* iters, const int8_t* tb_bits,
+                               const int8_t* ref_bits, int64_t bits_per_tb, int64_t bits_stride, int64_t* counters,
+                               nrldpc_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRLDPC_H */

@@ -1,0 +1,137 @@
+// libnrldpc: handle management, error reporting, host-side table queries (see include/nrldpc.h).
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nr_bg_tables.h"
+#include "nrldpc_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+void nr_set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* nrldpc_last_error(void) { return g_err; }
+extern "C" int nrldpc_version(void) { return NRLDPC_VERSION; }
+
+extern "C" int nrldpc_lifting_set_index(int zc)
+{
+    for (int i = 0; i < NR_NUM_LIFTING_SETS; i++)
+        for (int j = 0; j < 8; j++)
+            if (NR_LIFTING_SETS[i][j] == zc && zc > 0) return i;
+    return -1;
+}
+
+extern "C" int nrldpc_graph_info(int bg, int* rows, int* cols, int* sys_cols, int* edges)
+{
+    if (bg != 1 && bg != 2) { nr_set_error("'baseGraphNo' must be 1 or 2!"); return NRLDPC_ERR_ARG; }
+    if (rows) *rows = bg == 1 ? NR_BG1_ROWS : NR_BG2_ROWS;
+    if (cols) *cols = bg == 1 ? NR_BG1_COLS : NR_BG2_COLS;
+    if (sys_cols) *sys_cols = bg == 1 ? 22 : 10;
+    if (edges) *edges = bg == 1 ? NR_BG1_EDGES : NR_BG2_EDGES;
+    return NRLDPC_OK;
+}
+
+int nr_build_graph(int bg, int zc, NrGraph* g)
+{
+    if (bg != 1 && bg != 2) { nr_set_error("'baseGraphNo' must be 1 or 2!"); return NRLDPC_ERR_ARG; }
+    const int ils = nrldpc_lifting_set_index(zc);
+    if (ils < 0) { nr_set_error("illegal lifting size %d", zc); return NRLDPC_ERR_ARG; }
+    memset(g, 0, sizeof(*g));
+    g->P = bg == 1 ? NR_BG1_ROWS : NR_BG2_ROWS;
+    g->ncols = bg == 1 ? NR_BG1_COLS : NR_BG2_COLS;
+    g->ksys = bg == 1 ? 22 : 10;
+    g->ncore = g->ksys + 4;
+    g->Z = zc;
+    const uint8_t* deg = bg == 1 ? NR_BG1_ROW_DEG : NR_BG2_ROW_DEG;
+    const uint8_t* col = bg == 1 ? NR_BG1_COL : NR_BG2_COL;
+    const uint16_t* sh = bg == 1 ? NR_BG1_SHIFT[ils] : NR_BG2_SHIFT[ils];
+    int e = 0;
+    for (int i = 0; i < g->P; i++) {
+        g->rowEdge0[i] = (uint16_t)e;
+        for (int j = 0; j < deg[i]; j++, e++) g->edge[e] = ((uint32_t)col[e] << 16) | (uint32_t)(sh[e] % zc);
+    }
+    g->rowEdge0[g->P] = (uint16_t)e;
+    g->rowEdge0[g->P + 1] = (uint16_t)e;
+    return 0;
+}
+
+extern "C" int nrldpc_base_graph(int bg, int set_index, int zc, int16_t* out)
+{
+    if (bg != 1 && bg != 2) { nr_set_error("'baseGraphNo' must be 1 or 2!"); return NRLDPC_ERR_ARG; }
+    if (zc <= 0 || !out) { nr_set_error("base_graph: bad argument"); return NRLDPC_ERR_ARG; }
+    if (set_index < 0) set_index = nrldpc_lifting_set_index(zc);
+    if (set_index < 0 || set_index > 7) { nr_set_error("illegal lifting size %d", zc); return NRLDPC_ERR_ARG; }
+    const int P = bg == 1 ? NR_BG1_ROWS : NR_BG2_ROWS, n = bg == 1 ? NR_BG1_COLS : NR_BG2_COLS;
+    const uint8_t* deg = bg == 1 ? NR_BG1_ROW_DEG : NR_BG2_ROW_DEG;
+    const uint8_t* col = bg == 1 ? NR_BG1_COL : NR_BG2_COL;
+    const uint16_t* sh = bg == 1 ? NR_BG1_SHIFT[set_index] : NR_BG2_SHIFT[set_index];
+    for (int i = 0; i < P * n; i++) out[i] = -1;
+    int e = 0;
+    for (int i = 0; i < P; i++)
+        for (int j = 0; j < deg[i]; j++, e++) out[i * n + col[e]] = (int16_t)(sh[e] % zc);
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_create(int device, nrldpc_handle** out)
+{
+    if (!out) { nr_set_error("create: null out"); return NRLDPC_ERR_ARG; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        nr_set_error("no CUDA device available (%s); libnrldpc has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return NRLDPC_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { nr_set_error("create: device %d out of range", device); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NR_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        nr_set_error("device %d is sm_%d%d; libnrldpc is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return NRLDPC_ERR_CUDA;
+    }
+    nrldpc_handle* h = (nrldpc_handle*)calloc(1, sizeof(nrldpc_handle));
+    if (!h) return NRLDPC_ERR_NOMEM;
+    h->device = device;
+    h->numSMs = prop.multiProcessorCount;
+    h->maxSmemOptin = (int)prop.sharedMemPerBlockOptin;
+    h->smemPerSM = (int)prop.sharedMemPerMultiprocessor;
+    const char* occ = getenv("NRLDPC_DEC_OCC");
+    h->decOcc = occ ? atoi(occ) : 0;
+    e = cudaMalloc(&h->workCounter, 16 * sizeof(unsigned int));
+    if (e != cudaSuccess) { free(h); nr_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return NRLDPC_ERR_CUDA; }
+    cudaMemset(h->workCounter, 0, 16 * sizeof(unsigned int));
+    *out = h;
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_destroy(nrldpc_handle* h)
+{
+    if (!h) return NRLDPC_OK;
+    cudaSetDevice(h->device);
+    if (h->scratch) cudaFree(h->scratch);
+    if (h->tmp) cudaFree(h->tmp);
+    if (h->workCounter) cudaFree(h->workCounter);
+    free(h);
+    return NRLDPC_OK;
+}
+
+int nr_reserve_tmp(nrldpc_handle* h, size_t bytes, void** out)
+{
+    if (bytes > h->tmpBytes) {
+        if (h->tmp) NR_CUDA_CHECK(cudaFree(h->tmp));
+        h->tmp = nullptr;
+        h->tmpBytes = 0;
+        NR_CUDA_CHECK(cudaMalloc(&h->tmp, bytes));
+        h->tmpBytes = bytes;
+    }
+    *out = h->tmp;
+    return NRLDPC_OK;
+}

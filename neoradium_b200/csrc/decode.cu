@@ -1,0 +1,720 @@
+// K1: batched layered normalised min-sum decoder for the lifted QC parity-check matrices of TS 38.212 (BG1/BG2, every
+// Zc <= 384), with rate recovery fused into its load phase (K3b) and the CRC fused into its epilogue (K4).
+//
+// Replaces LdpcDecoder.decode (neoradium/ldpc.py:1535-1581) and, in fused mode, the chain
+// recoverRate -> decode -> checkCrcAndMerge (ldpc.py:1365-1418, 1610-1619; harq.py:165-173).
+//
+// Mapping (B200: 148 SMs, 227 KB shared memory / CTA, no tensor cores -- the work is not a contraction):
+//   * one THREAD per lifted check: thread (cb, m) owns check m of EVERY layer of code block cb.  A CTA hosts
+//     floor(384 / Zc) code blocks (1 at Zc >= 193), persistent over code-block groups.
+//   * posteriors of the `ncore` = k+4 columns of degree > 1 live in shared memory ([cb][col][Zc], conflict-free:
+//     consecutive m hit consecutive words (m + s) mod Zc).  Circulant shifts are index arithmetic only.
+//   * everything else is THREAD-PRIVATE and never needs a barrier: the posterior of the degree-1 extension-parity column
+//     of row i (its circulant is the identity, so lifted position m belongs to thread m) and the compressed
+//     check-to-variable messages (alpha*min1, alpha*min2, sign bits + argmin).  They sit in per-row state planes,
+//     in shared memory for as many rows as fit and in an L2-resident scratch for the rest.
+//   * per layer: gather t_j = r - old message, two-min/sign/argmin over the <= 19 edges in registers (row bodies are
+//     unrolled per degree, the (column, shift) table comes from the constant bank), scatter r = t + new, ONE barrier.
+//   * extension rows whose parity LLRs are all zero can never change any other column (their min1 is 0), so the
+//     schedule stops at the last row with a non-zero extension LLR; the beliefs of the skipped columns are produced
+//     in closed form in the epilogue.  This is exact, not an approximation (tests/test_decode_gpu.py).
+//
+// Bit-exactness discipline ("a10 formula"): every add/sub/mul is an explicit round-to-nearest intrinsic
+// (no FMA contraction), operation order t = r - old; new = (mag*sign)*0.75; r = t + new, sign(+-0) = +, first-index
+// argmin, the "+100000" second-minimum quirk, clip to +-1e10.  -0.0 inputs are canonicalised to +0.0 at load, which
+// makes the raw sign bit equal to (t < 0) for every t the recursion can produce.
+#include "nrldpc_internal.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// exact arithmetic helpers
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+struct FP;
+template <>
+struct FP<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ uint32_t sign(float a) { return __float_as_uint(a) >> 31; }
+    static __device__ __forceinline__ float flip(float mag, uint32_t bit)
+    {
+        return __uint_as_float(__float_as_uint(mag) ^ (bit << 31));
+    }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <>
+struct FP<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ uint32_t sign(double a) { return ((uint32_t)__double2hiint(a)) >> 31; }
+    static __device__ __forceinline__ double flip(double mag, uint32_t bit)
+    {
+        return __hiloint2double(__double2hiint(mag) ^ (int)(bit << 31), __double2loint(mag));
+    }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------------------------
+struct DecArgs {
+    // batch
+    long long numCb;
+    int cbPerCta;       // code blocks hosted by one CTA
+    int numIter;
+    int flags;
+    int numRows;        // rows scheduled (>= 4); rows >= numRows have all-zero extension LLRs
+    int smemRows;       // rows whose state planes live in shared memory; the rest go to `scratch`
+    int outCols;        // columns written to bits / beliefs
+    // mode A: rate-recovered input
+    const void* llr;
+    long long llrStride;
+    int inCols;
+    // mode B: fused rate recovery (rm != 0)
+    int rm;
+    int K, F, C, qm, ncb, k0, E0, nShort, fStep;   // per-TB split: first nShort blocks have E0, the rest E0+fStep
+    long long llrLen;   // valid LLRs per TB
+    void* softBuf;      // NULL or [numCb, ncb-F]
+    // outputs
+    signed char* bits;
+    long long bitsStride;
+    void* beliefs;
+    int* iters;
+    // fused CRC / merge (mode B)
+    signed char* tbBits;
+    long long tbBitsStride;
+    unsigned char* cbCrcOk;
+    unsigned int* cbRemA;    // per-CB CRC24A remainder of its payload (combined per TB by a second kernel)
+    // overflow state
+    void* scratch;
+    unsigned int* workCounter;
+};
+
+// per-row thread-private state planes (SoA: plane p of row slot s = base + (4 s + p) * nThreads elements of T)
+enum { PL_M1 = 0, PL_M2 = 1, PL_SW = 2, PL_REXT = 3, NPLANES = 4 };
+
+template <typename T>
+struct RowAccess {
+    T* base;   // plane 0 of this row for this thread (already offset by tid)
+    int nT;
+    __device__ __forceinline__ T ld(int plane) const { return base[(size_t)plane * nT]; }
+    __device__ __forceinline__ void st(int plane, T v) const { base[(size_t)plane * nT] = v; }
+    __device__ __forceinline__ uint32_t ldsw() const { return *reinterpret_cast<const uint32_t*>(base + (size_t)PL_SW * nT); }
+    __device__ __forceinline__ void stsw(uint32_t v) const { *reinterpret_cast<uint32_t*>(base + (size_t)PL_SW * nT) = v; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// one layer for one lifted check.  D = row degree, EXT = last edge is the thread-private extension column.
+// sw layout: bits 0..18 sign of the stored message per edge, bits 24..28 argmin edge.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int D, bool EXT, bool FIRST, bool SMEM_STATE>
+__device__ __forceinline__ void process_row(const NrGraph& g, int e0, T* __restrict__ rcb, int m, int Z,
+                                            const RowAccess<T>& st)
+{
+    T t[D];
+    int addr[D];
+    T m1s = (T)0, m2s = (T)0;
+    uint32_t sw = 0;
+    int oldIdx = 0;
+    if (!FIRST) {
+        m1s = st.ld(PL_M1);
+        m2s = st.ld(PL_M2);
+        sw = st.ldsw();
+        oldIdx = (int)(sw >> 24);
+    }
+    T min1 = (T)0, min2 = FP<T>::inf();
+    int idx = 0;
+    uint32_t nsw = 0;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        T rv;
+        if (EXT && j == D - 1) {
+            rv = st.ld(PL_REXT);
+            addr[j] = 0;
+        } else {
+            const uint32_t ew = g.edge[e0 + j];
+            int p = m + (int)(ew & 0xffffu);
+            p = (p >= Z) ? p - Z : p;
+            addr[j] = (int)(ew >> 16) * Z + p;
+            rv = rcb[addr[j]];
+        }
+        if (FIRST) {
+            t[j] = rv;   // old message is +0: r - 0 == r exactly
+        } else {
+            const T mag = (j == oldIdx) ? m2s : m1s;
+            t[j] = FP<T>::sub(rv, FP<T>::flip(mag, (sw >> j) & 1u));
+        }
+        const T a = FP<T>::abs(t[j]);
+        nsw |= FP<T>::sign(t[j]) << j;
+        if (j == 0) {
+            min1 = a;
+        } else {
+            const bool lt = a < min1;   // strict: keeps the FIRST minimum (np.argmin)
+            min2 = lt ? min1 : FP<T>::mn(min2, a);
+            min1 = lt ? a : min1;
+            idx = lt ? j : idx;
+        }
+    }
+    // the reference bumps the signed minimum by 1e5 and takes |.| before searching the second minimum (ldpc.py:1563)
+    {
+        const T tq = FP<T>::flip(min1, (nsw >> idx) & 1u);
+        min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(tq, (T)100000)));
+    }
+    const uint32_t par = __popc(nsw) & 1u;
+    const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;   // sign of new message j = sign_j * parity
+    m1s = FP<T>::mul(min1, (T)0.75);
+    m2s = FP<T>::mul(min2, (T)0.75);
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const T mag = (j == idx) ? m2s : m1s;
+        const T nv = FP<T>::add(t[j], FP<T>::flip(mag, (msw >> j) & 1u));
+        if (EXT && j == D - 1)
+            st.st(PL_REXT, nv);
+        else
+            rcb[addr[j]] = nv;
+    }
+    st.st(PL_M1, m1s);
+    st.st(PL_M2, m2s);
+    st.stsw(msw | ((uint32_t)idx << 24));
+}
+
+template <typename T, bool FIRST, bool SMEM_STATE>
+__device__ __forceinline__ void dispatch_row(const NrGraph& g, int row, T* rcb, int m, int Z, const RowAccess<T>& st)
+{
+    const int e0 = g.rowEdge0[row];
+    const int deg = g.rowEdge0[row + 1] - e0;
+    if (row >= 4) {
+        switch (deg) {
+            case 3: process_row<T, 3, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 4: process_row<T, 4, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 5: process_row<T, 5, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 6: process_row<T, 6, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 7: process_row<T, 7, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 8: process_row<T, 8, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 9: process_row<T, 9, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            default: process_row<T, 10, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+        }
+    } else {
+        switch (deg) {
+            case 8: process_row<T, 8, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 10: process_row<T, 10, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            default: process_row<T, 19, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GF(2) helpers for the fused CRC
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gf_shift1(uint32_t r, uint32_t poly, int c)
+{
+    const uint32_t top = (r >> (c - 1)) & 1u;
+    r = (r << 1) & ((1u << c) - 1u);
+    return top ? (r ^ poly) : r;
+}
+__device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b, uint32_t poly, int c)
+{
+    uint32_t r = 0;
+    for (int i = c - 1; i >= 0; i--) {
+        r = gf_shift1(r, poly, c);
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+
+// CRC remainder of `len` hard-decision bits of one code block, cooperatively by its Z threads.
+// bit i lives at rcb[i] (posterior < 0).  The message is right-aligned in Z chunks of B bits (leading zeros do not
+// change a zero-initialised CRC), per-thread remainders are merged pairwise: rem = left * x^(span) + right.
+// `tree` is per-CB scratch of >= nextPow2(Z) words.  Every thread of the CTA must call this (barriers inside).
+template <typename T>
+__device__ uint32_t cb_crc(const T* rcb, int len, int Z, int P2, int m, bool active, uint32_t* tree, uint32_t poly,
+                           int c)
+{
+    const int B = (len + Z - 1) / Z;
+    const int lead = B * Z - len;
+    if (active) {
+        uint32_t rem = 0;
+        const int i0 = m * B - lead;
+        for (int b = 0; b < B; b++) {
+            const int i = i0 + b;
+            const uint32_t bit = (i >= 0) ? FP<T>::sign(rcb[i]) : 0u;
+            const uint32_t fb = ((rem >> (c - 1)) & 1u) ^ bit;
+            rem = (rem << 1) & ((1u << c) - 1u);
+            if (fb) rem ^= poly;
+        }
+        tree[(P2 - Z) + m] = rem;
+        if (m < P2 - Z) tree[m] = 0;   // virtual leading chunks
+    }
+    uint32_t f = 1;   // x^B mod g
+    for (int b = 0; b < B; b++) f = gf_shift1(f, poly, c);
+    __syncthreads();
+    for (int span = 1; span < P2; span <<= 1) {
+        // worker w merges the pair of spans ending at right = (w+1)*2*span-1:  rem = left * x^(B*span) + right
+        const int right = (m + 1) * 2 * span - 1;
+        if (active && right < P2) tree[right] = gf_mulmod(tree[right - span], f, poly, c) ^ tree[right];
+        f = gf_mulmod(f, f, poly, c);
+        __syncthreads();
+    }
+    return active ? tree[P2 - 1] : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, typename TIn>
+__global__ void __launch_bounds__(384, 1)
+    nr_decode_kernel(const __grid_constant__ NrGraph g, const __grid_constant__ DecArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    const int Z = g.Z;
+    const int ncore = g.ncore;
+    const int nT = blockDim.x;
+    const int tid = threadIdx.x;
+    const int cbl = tid / Z;            // local code block
+    const int m = tid - cbl * Z;        // lifted check / position
+    const bool lane_ok = cbl < a.cbPerCta;
+
+    T* rs = reinterpret_cast<T*>(smemRaw);                                   // [cbPerCta][ncore][Z]
+    T* stateS = rs + (size_t)a.cbPerCta * ncore * Z;                         // [smemRows][NPLANES][nT]
+    uint32_t* misc = reinterpret_cast<uint32_t*>(stateS + (size_t)a.smemRows * NPLANES * nT);   // flags + crc tree
+    T* stateG = reinterpret_cast<T*>(a.scratch) + (size_t)blockIdx.x * (size_t)(a.numRows - a.smemRows) * NPLANES * nT;
+    T* rcb = rs + (size_t)cbl * ncore * Z;
+    const int ksys = g.ksys;
+    const int N = (g.ncols - 2) * Z;
+
+    const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
+    for (long long grp = blockIdx.x; grp < numGroups; grp += gridDim.x) {
+        const long long cb = grp * a.cbPerCta + cbl;
+        const bool active = lane_ok && cb < a.numCb;
+
+        // -------------------------------------------------------------------------------------------------------
+        // load phase: column block `col` (un-punctured index), position m.  Punctured columns 0,1 start at 0.
+        // -------------------------------------------------------------------------------------------------------
+        if (active) {
+            rcb[m] = (T)0;
+            rcb[Z + m] = (T)0;
+            const int lastCol = (a.numRows >= 4) ? (ksys + a.numRows) : ncore;   // exclusive
+            // fused rate-recovery parameters of this code block
+            int E = 0, L = 0, sysLen = 0, Eq = 1;
+            const TIn* x = nullptr;
+            T* sb = nullptr;
+            long long xAvail = 0;
+            if (a.rm) {
+                const long long tb = cb / a.C;
+                const int r = (int)(cb - tb * a.C);
+                E = a.E0 + (r >= a.nShort ? a.fStep : 0);
+                const long long off = (long long)r * a.E0 + (long long)(r > a.nShort ? (r - a.nShort) : 0) * a.fStep;
+                x = reinterpret_cast<const TIn*>(a.llr) + tb * a.llrStride + off;
+                xAvail = a.llrLen - off;   // LLRs actually present for this block (rest are zeros, ldpc.py:1402)
+                L = a.ncb - a.F;
+                sysLen = a.K - a.F - 2 * Z;
+                Eq = E / a.qm;
+                if (a.softBuf) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
+            }
+            for (int col = 2; col < lastCol; col++) {
+                const int n = (col - 2) * Z + m;   // index in the punctured coded block
+                T v = (T)0;
+                if (!a.rm) {
+                    if (col - 2 < a.inCols) v = (T)reinterpret_cast<const TIn*>(a.llr)[cb * a.llrStride + n];
+                } else if (n < a.ncb) {
+                    if (n >= sysLen && n < sysLen + a.F) {
+                        v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
+                    } else {
+                        const int q = (n < sysLen) ? n : n - a.F;   // index in the filler-less circular buffer
+                        T acc = sb ? sb[q] : (T)0;
+                        int i = q - a.k0;
+                        if (i < 0) i += L;
+                        for (; i < E; i += L) {       // one term per wrap, ascending => the reference's += order
+                            const int s = i % Eq, b = i / Eq;   // de-interleave: stream index s*qm + b
+                            const long long xi = (long long)s * a.qm + b;
+                            const T xv = (xi < xAvail) ? (T)x[xi] : (T)0;
+                            acc = FP<T>::add(acc, xv);
+                        }
+                        if (sb) sb[q] = acc;
+                        v = acc;
+                    }
+                }
+                v = (v > (T)1e10) ? (T)1e10 : v;        // np.clip(., -1e10, 1e10), ldpc.py:1536
+                v = (v < (T)-1e10) ? (T)-1e10 : v;
+                v = FP<T>::add(v, (T)0);                 // -0.0 -> +0.0 (see header)
+                if (col < ncore) {
+                    rcb[col * Z + m] = v;
+                } else {
+                    const int row = col - ksys;
+                    T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
+                                                 : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
+                    base[(size_t)PL_REXT * nT] = v;
+                }
+            }
+            if (a.rm && sb) {
+                // soft-buffer positions beyond the scheduled rows still have to be combined (HARQ keeps them)
+                for (int col = lastCol; col < g.ncols; col++) {
+                    const int n = (col - 2) * Z + m;
+                    if (n >= a.ncb || (n >= sysLen && n < sysLen + a.F)) continue;
+                    const int q = (n < sysLen) ? n : n - a.F;
+                    T acc = sb[q];
+                    int i = q - a.k0;
+                    if (i < 0) i += L;
+                    for (; i < E; i += L) {
+                        const int s = i % Eq, b = i / Eq;
+                        const long long xi = (long long)s * a.qm + b;
+                        acc = FP<T>::add(acc, (xi < xAvail) ? (T)x[xi] : (T)0);
+                    }
+                    sb[q] = acc;
+                }
+            }
+        }
+        __syncthreads();
+
+        // -------------------------------------------------------------------------------------------------------
+        // iterations
+        // -------------------------------------------------------------------------------------------------------
+        int itersDone = 0;
+        bool cbDone = false;
+        for (int it = 0; it < a.numIter; it++) {
+            for (int row = 0; row < a.numRows; row++) {
+                if (active && !cbDone) {
+                    if (row < a.smemRows) {
+                        RowAccess<T> st{stateS + (size_t)row * NPLANES * nT + tid, nT};
+                        if (it == 0)
+                            dispatch_row<T, true, true>(g, row, rcb, m, Z, st);
+                        else
+                            dispatch_row<T, false, true>(g, row, rcb, m, Z, st);
+                    } else {
+                        RowAccess<T> st{stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid, nT};
+                        if (it == 0)
+                            dispatch_row<T, true, false>(g, row, rcb, m, Z, st);
+                        else
+                            dispatch_row<T, false, false>(g, row, rcb, m, Z, st);
+                    }
+                }
+                __syncthreads();
+            }
+            if (!cbDone) itersDone = it + 1;
+            if (a.flags & NRLDPC_DEC_EARLY_STOP) {
+                // syndrome of the hard decisions after a COMPLETE iteration, all scheduled rows (skipped rows are
+                // satisfied by construction: their parity bit is the parity of the rest)
+                uint32_t bad = 0;
+                if (active && !cbDone) {
+                    for (int row = 0; row < a.numRows; row++) {
+                        const int e0 = g.rowEdge0[row];
+                        const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
+                        uint32_t par = 0;
+                        for (int e = e0; e < e1; e++) {
+                            const uint32_t ew = g.edge[e];
+                            int p = m + (int)(ew & 0xffffu);
+                            p = (p >= Z) ? p - Z : p;
+                            par ^= FP<T>::sign(rcb[(int)(ew >> 16) * Z + p]);
+                        }
+                        if (row >= 4) {
+                            const T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
+                                                               : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
+                            par ^= FP<T>::sign(base[(size_t)PL_REXT * nT]);
+                        }
+                        bad |= par;
+                    }
+                }
+                if (tid < a.cbPerCta) misc[tid] = 0;
+                __syncthreads();
+                if (bad) misc[cbl] = 1;
+                __syncthreads();
+                if (lane_ok && misc[cbl] == 0) cbDone = true;
+                // CTA-wide exit when every hosted block is done
+                const int anyLeft = __syncthreads_or((active && !cbDone) ? 1 : 0);
+                if (!anyLeft) break;
+            }
+        }
+
+        // -------------------------------------------------------------------------------------------------------
+        // epilogue: hard decisions / beliefs, closed form for skipped extension columns, fused CRC + merge
+        // -------------------------------------------------------------------------------------------------------
+        if (active) {
+            if (a.iters && m == 0) a.iters[cb] = itersDone;
+            const int outCore = min(a.outCols, ncore);
+            if (a.bits) {
+                signed char* o = a.bits + cb * a.bitsStride;
+                for (int col = 0; col < outCore; col++) o[col * Z + m] = (signed char)FP<T>::sign(rcb[col * Z + m]);
+            }
+            if (a.beliefs) {
+                T* o = reinterpret_cast<T*>(a.beliefs) + cb * (long long)a.outCols * Z;
+                for (int col = 0; col < outCore; col++) o[col * Z + m] = rcb[col * Z + m];
+            }
+            for (int col = ncore; col < a.outCols; col++) {
+                const int row = col - ksys;
+                T v;
+                if (row < a.numRows) {
+                    const T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
+                                                       : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
+                    v = base[(size_t)PL_REXT * nT];
+                } else {
+                    // skipped row: t_ext == 0 in every iteration, so its belief after the last iteration is
+                    // 0.75 * parity * min(min_j |r_j|, 1e5) over the row's core edges evaluated on the final posteriors
+                    const int e0 = g.rowEdge0[row];
+                    const int e1 = g.rowEdge0[row + 1] - 1;
+                    T mn = (T)100000;
+                    uint32_t par = 0;
+                    for (int e = e0; e < e1; e++) {
+                        const uint32_t ew = g.edge[e];
+                        int p = m + (int)(ew & 0xffffu);
+                        p = (p >= Z) ? p - Z : p;
+                        const T rv = rcb[(int)(ew >> 16) * Z + p];
+                        mn = FP<T>::mn(mn, FP<T>::abs(rv));
+                        par ^= FP<T>::sign(rv);
+                    }
+                    v = (a.numIter > 0) ? FP<T>::flip(FP<T>::mul(mn, (T)0.75), par) : (T)0;
+                    v = FP<T>::add(v, (T)0);
+                }
+                if (a.bits) a.bits[cb * a.bitsStride + col * Z + m] = (signed char)(v < (T)0);
+                if (a.beliefs) reinterpret_cast<T*>(a.beliefs)[cb * (long long)a.outCols * Z + col * Z + m] = v;
+            }
+        }
+        if (a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA)) {
+            // checkCrcAndMerge (ldpc.py:1610-1619) on the hard decisions still in shared memory
+            const int Lk = a.K - a.F;                       // code block without fillers
+            const int per = (a.C > 1) ? Lk - 24 : Lk;       // payload copied into the merged transport block
+            int P2 = 1;
+            while (P2 < Z) P2 <<= 1;
+            uint32_t* tree = misc + ((a.cbPerCta + 31) & ~31) + (size_t)cbl * P2;
+            const NrCrcPoly pb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
+            const uint32_t remCb = cb_crc<T>(rcb, Lk, Z, P2, m, active, tree, pb.poly, pb.len);
+            __syncthreads();
+            uint32_t remA = remCb;
+            if (a.C > 1) {
+                const NrCrcPoly pa = nr_crc_poly(NRLDPC_CRC24A);
+                remA = cb_crc<T>(rcb, per, Z, P2, m, active, tree, pa.poly, pa.len);
+            }
+            if (active) {
+                if (m == 0) {
+                    if (a.cbCrcOk) a.cbCrcOk[cb] = (remCb == 0);
+                    if (a.cbRemA) a.cbRemA[cb] = remA;
+                }
+                if (a.tbBits) {
+                    const long long tb = cb / a.C;
+                    const int r = (int)(cb - tb * a.C);
+                    signed char* o = a.tbBits + tb * a.tbBitsStride + (long long)r * per;
+                    for (int i = m; i < per; i += Z) o[i] = (signed char)FP<T>::sign(rcb[i]);
+                }
+            }
+        }
+        __syncthreads();   // shared memory is reused by the next group
+    }
+}
+
+// combine per-code-block CRC24A remainders into the transport-block check: rem = sum_r rem_r * x^(per*(C-1-r))
+__global__ void nr_tb_crc_kernel(const unsigned int* cbRemA, long long numTb, int C, int per, unsigned char* tbOk)
+{
+    const long long tb = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tb >= numTb) return;
+    const NrCrcPoly pa = nr_crc_poly(NRLDPC_CRC24A);
+    uint32_t f = 1;   // x^per mod g by square and multiply
+    {
+        uint32_t base = 2;   // x
+        int e = per;
+        while (e) {
+            if (e & 1) f = gf_mulmod(f, base, pa.poly, pa.len);
+            base = gf_mulmod(base, base, pa.poly, pa.len);
+            e >>= 1;
+        }
+    }
+    uint32_t rem = 0;
+    for (int r = 0; r < C; r++) rem = gf_mulmod(rem, f, pa.poly, pa.len) ^ cbRemA[tb * C + r];
+    tbOk[tb] = (rem == 0);
+}
+
+// last column (punctured frame) holding a non-zero LLR, max over the batch -> numRows for mode A
+template <typename TIn>
+__global__ void nr_last_nonzero_kernel(const TIn* llr, long long numCb, long long stride, int len, int Z, int* lastCol)
+{
+    int best = -1;
+    const long long total = numCb * (long long)len;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long cb = i / len;
+        const int n = (int)(i - cb * len);
+        if (llr[cb * stride + n] != (TIn)0) best = max(best, n / Z);
+    }
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(lastCol, best);
+}
+
+template <typename T, typename TIn>
+int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s)
+{
+    const int Z = g.Z;
+    a.cbPerCta = max(1, 384 / Z);
+    if ((long long)a.cbPerCta > a.numCb) a.cbPerCta = (int)a.numCb;
+    int nT = a.cbPerCta * Z;
+    nT = (nT + 31) & ~31;
+    const size_t rBytes = (size_t)a.cbPerCta * g.ncore * Z * sizeof(T);
+    const size_t rowBytes = (size_t)NPLANES * nT * sizeof(T);
+    int P2 = 1;
+    while (P2 < Z) P2 <<= 1;
+    const size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + (size_t)a.cbPerCta * P2) * sizeof(uint32_t);
+    const size_t avail = (size_t)h->maxSmemOptin - 1024;
+    if (rBytes + miscBytes > avail) {
+        nr_set_error("decode: posteriors do not fit shared memory");
+        return NRLDPC_ERR_ARG;
+    }
+    int smemRows = (int)((avail - rBytes - miscBytes) / rowBytes);
+    if (smemRows > a.numRows) smemRows = a.numRows;
+    a.smemRows = smemRows;
+    const size_t smem = rBytes + (size_t)smemRows * rowBytes + miscBytes;
+    const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
+    // resident CTAs per SM are bounded by shared memory and by 2048 threads
+    int perSM = (int)(avail / (smem + 1024));
+    perSM = max(1, min(perSM, 2048 / nT));
+    long long grid = min(numGroups, (long long)h->numSMs * perSM);
+    const size_t needScratch = (size_t)grid * (size_t)(a.numRows - smemRows) * rowBytes;
+    if (needScratch > h->scratchBytes) {
+        if (h->scratch) NR_CUDA_CHECK(cudaFree(h->scratch));
+        h->scratch = nullptr;
+        h->scratchBytes = 0;
+        NR_CUDA_CHECK(cudaMalloc(&h->scratch, needScratch));
+        h->scratchBytes = needScratch;
+    }
+    a.scratch = h->scratch;
+    auto kern = nr_decode_kernel<T, TIn>;
+    NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, nT, smem, s>>>(g, a);
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+int dispatch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, int inDtype, int computeDtype, cudaStream_t s)
+{
+    if (computeDtype == NRLDPC_F32 && inDtype == NRLDPC_F32) return launch_decode<float, float>(h, g, a, s);
+    if (computeDtype == NRLDPC_F32 && inDtype == NRLDPC_F64) return launch_decode<float, double>(h, g, a, s);
+    if (computeDtype == NRLDPC_F64 && inDtype == NRLDPC_F64) return launch_decode<double, double>(h, g, a, s);
+    if (computeDtype == NRLDPC_F64 && inDtype == NRLDPC_F32) return launch_decode<double, float>(h, g, a, s);
+    nr_set_error("decode: bad dtype");
+    return NRLDPC_ERR_ARG;
+}
+
+}   // namespace
+
+// =================================================================================================================
+// C-ABI
+// =================================================================================================================
+extern "C" int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr,
+                             int64_t num_cb, int64_t llr_stride, int in_cols, int num_iter, int flags, int out_cols,
+                             int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("decode: null handle"); return NRLDPC_ERR_ARG; }
+    NrGraph g;
+    if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
+    if (num_cb <= 0 || in_cols < 0 || in_cols > g.ncols - 2 || out_cols < 1 || out_cols > g.ncols || num_iter < 0 ||
+        llr_stride < (int64_t)in_cols * zc) {
+        nr_set_error("decode: bad shape (num_cb=%lld in_cols=%d out_cols=%d stride=%lld)", (long long)num_cb, in_cols,
+                     out_cols, (long long)llr_stride);
+        return NRLDPC_ERR_ARG;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    DecArgs a{};
+    a.numCb = num_cb;
+    a.numIter = num_iter;
+    a.flags = flags;
+    a.llr = llr;
+    a.llrStride = llr_stride;
+    a.inCols = in_cols;
+    a.outCols = out_cols;
+    a.bits = (signed char*)bits;
+    a.bitsStride = (long long)out_cols * zc;
+    a.beliefs = beliefs;
+    a.iters = iters;
+    a.numRows = g.P;
+    if (!(flags & NRLDPC_DEC_ALL_ROWS)) {
+        // exact row skipping: find the last column with any non-zero LLR (one tiny pass over the input, 4 B D2H)
+        int* d = reinterpret_cast<int*>(h->workCounter) + 1;
+        int init = -1;
+        NR_CUDA_CHECK(cudaMemcpyAsync(d, &init, sizeof(int), cudaMemcpyHostToDevice, s));
+        const int len = in_cols * zc;
+        if (len > 0) {
+            const long long total = num_cb * (long long)len;
+            const int blocks = (int)min((long long)h->numSMs * 8, (total + 255) / 256);
+            if (in_dtype == NRLDPC_F32)
+                nr_last_nonzero_kernel<float><<<blocks, 256, 0, s>>>((const float*)llr, num_cb, llr_stride, len, zc, d);
+            else
+                nr_last_nonzero_kernel<double><<<blocks, 256, 0, s>>>((const double*)llr, num_cb, llr_stride, len, zc, d);
+            NR_CUDA_CHECK(cudaGetLastError());
+        }
+        int last = -1;
+        NR_CUDA_CHECK(cudaMemcpyAsync(&last, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+        NR_CUDA_CHECK(cudaStreamSynchronize(s));
+        const int lastFull = last + 2;                     // un-punctured column index
+        int rows = lastFull - g.ksys + 1;                  // row owning that extension column
+        a.numRows = max(4, min(g.P, rows));
+    }
+    return dispatch_decode(h, g, a, in_dtype, compute_dtype, s);
+}
+
+extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,
+                                const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride,
+                                void* soft_buffer, int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride,
+                                uint8_t* cb_crc_ok, uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream)
+{
+    if (!h || !cfg) { nr_set_error("decode_tb: null argument"); return NRLDPC_ERR_ARG; }
+    NrGraph g;
+    if (nr_build_graph(cfg->bg, cfg->zc, &g)) return NRLDPC_ERR_ARG;
+    const int Z = cfg->zc, N = (g.ncols - 2) * Z;
+    {
+        const int rc = nr_check_tb_config(cfg, g, "decode_tb");
+        if (rc) return rc;
+    }
+    if (num_tb <= 0 || llr_len < 0 || llr_stride < llr_len) { nr_set_error("decode_tb: bad shape"); return NRLDPC_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    DecArgs a{};
+    a.numCb = num_tb * cfg->C;
+    a.numIter = num_iter;
+    a.flags = flags;
+    a.llr = llr;
+    a.llrStride = llr_stride;
+    a.llrLen = llr_len;
+    a.rm = 1;
+    a.K = cfg->K; a.F = cfg->F; a.C = cfg->C; a.qm = cfg->qm; a.ncb = cfg->ncb;
+    nr_tb_split(cfg, N, &a.E0, &a.nShort, &a.fStep, &a.k0);
+    a.softBuf = soft_buffer;
+    a.outCols = g.ksys;
+    a.iters = iters;
+    a.tbBits = (signed char*)tb_bits;
+    a.tbBitsStride = tb_bits_stride;
+    a.cbCrcOk = cb_crc_ok;
+    const int Lk = cfg->K - cfg->F, per = cfg->C > 1 ? Lk - 24 : Lk;
+    // per-CB CRC24A partials for the transport-block check
+    unsigned int* remA = nullptr;
+    if (tb_crc_ok) {
+        void* p = nullptr;
+        int rc0 = nr_reserve_tmp(h, (size_t)a.numCb * sizeof(unsigned int), &p);
+        if (rc0) return rc0;
+        remA = (unsigned int*)p;
+    }
+    a.cbRemA = remA;
+    // rows to schedule: with no soft buffer the LLR support is known in closed form; with a soft buffer (HARQ
+    // history unknown to the host) every row is scheduled.
+    a.numRows = g.P;
+    if (!soft_buffer && !(flags & NRLDPC_DEC_ALL_ROWS)) {
+        const int L = cfg->ncb - cfg->F;
+        const int Emax = a.E0 + ((a.nShort < cfg->C) ? a.fStep : 0);
+        int lastQ;   // last circular-buffer index written
+        if (a.k0 + Emax >= L) lastQ = L - 1; else lastQ = a.k0 + Emax - 1;
+        const int sysLen = cfg->K - cfg->F - 2 * Z;
+        const int lastN = (lastQ < sysLen) ? lastQ : lastQ + cfg->F;
+        const int lastFull = lastN / Z + 2;
+        a.numRows = max(4, min(g.P, lastFull - g.ksys + 1));
+    }
+    int rc = dispatch_decode(h, g, a, in_dtype, compute_dtype, s);
+    if (rc) return rc;
+    if (tb_crc_ok) {
+        const int blocks = (int)((num_tb + 127) / 128);
+        nr_tb_crc_kernel<<<blocks, 128, 0, s>>>(remA, num_tb, cfg->C, per, tb_crc_ok);
+        NR_CUDA_CHECK(cudaGetLastError());
+    }
+    return NRLDPC_OK;
+}
