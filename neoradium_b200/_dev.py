@@ -14,11 +14,12 @@ def device():
 
 
 def stream_ptr():
+    device()
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def handle():
-    return _native.handle(torch.cuda.current_device())
+    return _native.handle(device().index)
 
 
 def to_dev(arr, dtype=None):

@@ -1,0 +1,137 @@
+"""Device-resident batched front end of libnrldpc for throughput work (BLER sweeps, benchmarks, multi-GPU sharding).
+
+``TbBatchCodec`` handles a batch of EQUALLY configured transport blocks (same base graph, A, G, modulation, layers) --
+configs 2, 4 and 5 of BASELINE.json; mixed batches (config 3) are a Python-level loop over one codec per group.
+Inputs and outputs are CUDA torch tensors (PyTorch only carries the buffers); every operation is one C-ABI call of
+include/nrldpc.h.  The operation sequence is the reference's: TX = appendCrc('24A') -> doSegmentation -> encode ->
+rateMatch (ldpc.py:1200-1204); RX = recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') (ldpc.py:1234-1251).
+"""
+import math
+
+import torch
+
+from . import _dev, _native, params
+
+
+class TbBatchCodec:
+    def __init__(self, baseGraphNo, modulation, txBlockSize, g, txLayers=1, nRef=0, rv=0, precision='fp32',
+                 earlyStop=False, device=None):
+        if baseGraphNo not in (1, 2):
+            raise ValueError("'baseGraphNo' must be 1 or 2!")
+        if modulation not in params.MOD_ORDER:
+            raise ValueError("Invalid 'modulation' value!")
+        if rv not in (0, 1, 2, 3):
+            raise ValueError("Invalid 'rv' value! It must be one of 0, 1, 2, or 3.")
+        self.bg, self.qm, self.nl, self.nRef, self.rv = baseGraphNo, params.MOD_ORDER[modulation], txLayers, nRef, rv
+        self.A, self.G = int(txBlockSize), int(g)
+        self.B = self.A + 24
+        self.C, self.Zc, self.iLS, self.K = params.segmentation_params(self.bg, self.B)
+        per = int(math.ceil(self.B / self.C))
+        self.F = self.K - per - (24 if self.C > 1 else 0)
+        self.per = self.K - self.F - (24 if self.C > 1 else 0)         # payload bits per code block in the merged TB
+        self.N = (66 if self.bg == 1 else 50) * self.Zc
+        self.ncb = self.N if nRef == 0 else min(self.N, nRef)
+        self.lens = params.rate_matched_cb_lens(self.G, self.C, self.nl, self.qm)
+        self.sumE = int(sum(self.lens))
+        self.precision = precision
+        self.earlyStop = earlyStop
+        self.device = device if device is not None else _dev.device()
+        self.cfg = _native.TbConfig(bg=self.bg, zc=self.Zc, K=self.K, F=self.F, C=self.C, qm=self.qm, nl=self.nl,
+                                    ncb=self.ncb, rv=self.rv, reserved=0, G=self.G)
+        self._h = _native.handle(self.device.index if self.device.index is not None else torch.cuda.current_device())
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def encode(self, payload):
+        """payload int8 [numTb, A] (device) -> rate-matched bits int8 [numTb, sumE]."""
+        L = _native.lib()
+        s = _dev.stream_ptr()
+        numTb = payload.shape[0]
+        assert payload.shape[1] == self.A and payload.dtype == torch.int8 and payload.is_contiguous()
+        dev = payload.device
+        tb = torch.empty((numTb, self.B), dtype=torch.int8, device=dev)
+        _native.check(L.nrldpc_crc_attach(self._h, _dev.ptr(payload), numTb, self.A, self.A, _native.CRC_IDS['24A'],
+                                          _dev.ptr(tb), s))
+        cbs = torch.empty((numTb * self.C, self.K), dtype=torch.int8, device=dev)
+        _native.check(L.nrldpc_segment(self._h, self.cfg, _dev.ptr(tb), numTb, self.B, self.B, _dev.ptr(cbs), s))
+        coded = torch.empty((numTb * self.C, self.N), dtype=torch.int8, device=dev)
+        _native.check(L.nrldpc_encode(self._h, self.bg, self.Zc, _dev.ptr(cbs), numTb * self.C, _dev.ptr(coded), 1, s))
+        out = torch.empty((numTb, self.sumE), dtype=torch.int8, device=dev)
+        _native.check(L.nrldpc_rate_match(self._h, self.cfg, _dev.ptr(coded), numTb, _dev.ptr(out), self.sumE, s))
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def alloc_outputs(self, numTb):
+        dev = self.device
+        return dict(tb=torch.empty((numTb, self.C * self.per), dtype=torch.int8, device=dev),
+                    cbOk=torch.empty((numTb, self.C), dtype=torch.uint8, device=dev),
+                    tbOk=torch.empty((numTb,), dtype=torch.uint8, device=dev),
+                    iters=torch.empty((numTb, self.C), dtype=torch.int32, device=dev))
+
+    def decode(self, llr, numIter, out=None, softBuffer=None):
+        """llr float32|float64 [numTb, >=G'] (device, row pitch = stride(0)) -> dict(tb, cbOk, tbOk, iters).
+        One fused kernel pass (+ a tiny per-TB CRC combine) on the current stream; nothing is synchronised."""
+        numTb = llr.shape[0]
+        if out is None:
+            out = self.alloc_outputs(numTb)
+        flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
+        _native.check(_native.lib().nrldpc_decode_tb(
+            self._h, self.cfg, _native.F64 if llr.dtype == torch.float64 else _native.F32,
+            _native.F64 if self.precision == 'fp64' else _native.F32, _dev.ptr(llr), numTb, llr.shape[1],
+            llr.stride(0), _dev.ptr(softBuffer), int(numIter), flags, _dev.ptr(out['tb']), self.C * self.per,
+            _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']), _dev.ptr(out['iters']), _dev.stream_ptr()))
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def accumulate(self, out, counters, refPayload=None):
+        """counters int64[8] += {CBs, CB CRC fails, TBs, TB CRC fails, bit errors, sum iterations, 0, 0}."""
+        numTb = out['tb'].shape[0]
+        if refPayload is not None:
+            assert refPayload.shape[1] == self.A and refPayload.stride(0) == self.A
+            # compare the first A bits of each merged block; both are addressed with their own pitch via two calls
+            ref = torch.zeros_like(out['tb'])
+            ref[:, :self.A] = refPayload
+        else:
+            ref = None
+        _native.check(_native.lib().nrldpc_accumulate_counters(
+            self._h, numTb, self.C, _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']), _dev.ptr(out['iters']),
+            _dev.ptr(out['tb']) if ref is not None else None, _dev.ptr(ref), self.A, self.C * self.per,
+            _dev.ptr(counters), _dev.stream_ptr()))
+        return counters
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Synthetic channel for workload generation (NOT the hot path; plain torch ops, outside every timed region):
+# Gray-mapped QAM of TS 38.211 5.1 (neoradium/modulation.py:60-74), complex AWGN, max-log LLR (modulation.py:190-204),
+# positive LLR => bit 0.
+# ----------------------------------------------------------------------------------------------------------------------
+def qam_awgn_llr(bits, qm, snr_db, generator=None, dtype=torch.float32):
+    """bits int8 [..., n*qm] -> max-log LLRs [..., n*qm] after unit-energy QAM + AWGN at Es/N0 = snr_db."""
+    assert qm in (2, 4, 6, 8, 10), "BPSK is not needed by the workloads"
+    half = qm // 2
+    shp = bits.shape
+    b = bits.reshape(-1, qm).to(torch.float64)
+    scale = 1.0 / math.sqrt({2: 2, 4: 10, 6: 42, 8: 170, 10: 682}[qm])
+    n0 = 10.0 ** (-snr_db / 10.0)
+
+    def pam(bb):   # bb [..., half]: amplitude recursion of 38.211 (real part uses bits 0,2,4,.. imag 1,3,5,..)
+        a = torch.ones(bb.shape[0], dtype=torch.float64, device=bits.device)
+        for q in range(half - 1, 0, -1):
+            a = (1 << (half - q)) - (1 - 2 * bb[:, q]) * a
+        return (1 - 2 * bb[:, 0]) * a
+
+    re = pam(b[:, 0::2]) * scale
+    im = pam(b[:, 1::2]) * scale
+    noise = torch.randn((2, re.shape[0]), dtype=torch.float64, device=bits.device, generator=generator) * math.sqrt(n0 / 2)
+    yr, yi = re + noise[0], im + noise[1]
+    # per-dimension PAM levels and their bit labels
+    lv = torch.arange(1 << half, device=bits.device)
+    lb = ((lv[:, None] >> torch.arange(half - 1, -1, -1, device=bits.device)[None, :]) & 1).to(torch.float64)
+    levels = pam(lb) * scale                                              # [2^half]
+    out = torch.empty((re.shape[0], qm), dtype=torch.float64, device=bits.device)
+    for comp, y in ((0, yr), (1, yi)):
+        d2 = (y[:, None] - levels[None, :]) ** 2                          # [n, 2^half]
+        for q in range(half):
+            m0 = torch.where(lb[None, :, q] == 0, d2, torch.inf).min(1).values
+            m1 = torch.where(lb[None, :, q] == 1, d2, torch.inf).min(1).values
+            out[:, 2 * q + comp] = (m1 - m0) / n0
+    return out.reshape(shp).to(dtype)

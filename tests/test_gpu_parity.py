@@ -1,0 +1,381 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the Python drop-in classes and the C-ABI, against
+the CPU oracle on the same seeded inputs and against the committed golden fixtures.  Bit-exact for bits, indices and
+float64 beliefs; fp32 beliefs are compared bit-for-bit against the fp32 evaluation of the reference algorithm (the
+1e-4 tolerance of north_star is therefore slack, asserted as exact equality)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import nr_link
+import nr_oracle as O
+import nr_oracle_c as OC
+from conftest import MOD_NAME
+from neoradium_b200 import ChanCodeBase, LdpcDecoder, LdpcEncoder, _dev, _native
+from neoradium_b200.batch import TbBatchCodec, qam_awgn_llr
+
+pytestmark = pytest.mark.gpu
+
+
+class Harq:
+    def __init__(self, rv=0):
+        self.rv, self.decBuffer = rv, None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def test_matlab_golden_flow_on_gpu(matlab):
+    """Playground/CompareWithMatlab/LDPC/LDPC-Matlab.ipynb replayed on the CUDA path (all seven .mat comparisons)."""
+    in_bits = matlab["in"].reshape(-1)
+    enc = LdpcEncoder(baseGraphNo=1, modulation='QPSK', txLayers=1, nRef=0, targetRate=449 / 1024)
+    tbc = enc.appendCrc(in_bits, '24A')
+    assert tbc.shape == (10024,)
+    cbs = enc.doSegmentation(tbc)
+    assert (enc.liftingSize, enc.setIndex, enc.numFillerBits) == (240, 7, 244)
+    fs = enc.codeBlockSize - enc.numFillerBits
+    cbs_m = cbs.copy()
+    cbs_m[:, fs:] = -1
+    assert np.abs(cbs_m - matlab["cbsIn"].T).sum() == 0
+    full = enc.encode(cbs, puncture=False)
+    assert (enc.isValidCodedBlock(full[0]), enc.isValidCodedBlock(full[1]), enc.isValidCodedBlock(np.zeros(68 * 240)),
+            enc.isValidCodedBlock(np.ones(68 * 240))) == (True, True, True, False)
+    coded = enc.encode(cbs)
+    coded_m = coded.copy()
+    coded_m[:, fs - 480:fs - 480 + 244] = -1
+    assert np.abs(coded_m - matlab["enc"].T).sum() == 0
+    rm = enc.rateMatch(coded)
+    assert np.abs(rm - matlab["chIn"].reshape(-1)).sum() == 0
+    assert np.abs(enc.getRateMatchedCodeBlocks(in_bits) - matlab["chIn"].reshape(-1)).sum() == 0
+    ch = 1 - 2.0 * rm
+    dec = LdpcDecoder(baseGraphNo=1, modulation='QPSK', txLayers=1, nRef=0)
+    rr = dec.recoverRate(ch, len(in_bits))
+    rr_m = matlab["raterec"].T.copy()
+    rr_m[rr_m == np.inf] = LdpcDecoder.LARGE_LLR
+    assert rr.dtype == np.float64 and np.abs(rr - rr_m).sum() == 0
+    bits = dec.decode(rr)
+    assert bits.dtype == np.int8 and np.abs(bits - matlab["decBits"].T).sum() == 0
+    tb, ok = dec.checkCrcAndMerge(bits)
+    assert list(ok) == [True, True] and np.abs(tb - matlab["decBlk"].reshape(-1)).sum() == 0
+    assert dec.checkCrc(tb, '24A')
+    assert np.abs(tb[:-24] - in_bits).sum() == 0
+    # fused chain, both precisions
+    for prec in ("fp64", "fp32"):
+        d2 = LdpcDecoder(1, 'QPSK', precision=prec)
+        out, cbok, tbok = d2.decodeLLRs(ch, len(in_bits), 5)
+        assert np.array_equal(out, in_bits) and all(cbok) and tbok
+
+
+def test_crc24c_matlab_vector(matlab):
+    msg = matlab["polar_msg"].reshape(-1).astype(np.int8)
+    assert np.array_equal(ChanCodeBase.appendCrc(msg, '24C'), matlab["polar_msgcrc"].reshape(-1))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _fixture_names():
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_cases.npz"))
+    return [str(n) for n in z["names"]]
+
+
+@pytest.mark.parametrize("name", _fixture_names())
+def test_reference_fixtures_on_gpu(ref_cases, name):
+    """Outputs of the UNMODIFIED reference (committed fixtures): every stage bit-exact, float64 beliefs bit-exact,
+    HARQ soft buffers bit-exact over the rv sequence."""
+    cases, _ = ref_cases
+    d = cases[name]
+    bg, A, nl, nref, g = d["bg"], d["A"], d["nl"], d["nref"], d["g"]
+    enc = LdpcEncoder(bg, MOD_NAME[d["qm"]], nl, nref, 0.5)
+    cbs = enc.doSegmentation(enc.appendCrc(d["tb"], '24A'))
+    assert (enc.numCodeBlocks, enc.liftingSize, enc.setIndex, enc.codeBlockSize, enc.numFillerBits) == \
+        (d["C"], d["Zc"], d["iLS"], d["K"], d["F"])
+    assert np.array_equal(cbs, d["cbs"])
+    coded = enc.encode(cbs)
+    assert np.array_equal(coded, d["coded"])
+    dec = LdpcDecoder(bg, MOD_NAME[d["qm"]], nl, nref)          # fp64 = the reference's arithmetic
+    dec32 = LdpcDecoder(bg, MOD_NAME[d["qm"]], nl, nref, precision='fp32')
+    dec32.initialize(A + 24)
+    h, hf = Harq(), Harq()
+    for t, rv in enumerate(d["rvs"]):
+        rv = int(rv)
+        assert np.array_equal(enc.rateMatch(coded, g, True, rv), d["rm%d" % t])
+        llr = d["llr%d" % t].astype(np.float64)
+        h.rv = hf.rv = rv
+        rr = dec.recoverRate(llr, A, h)
+        assert np.array_equal(h.decBuffer, d["decbuf%d" % t])
+        bel = dec.decode(rr, d["nit"], False, True)
+        assert np.array_equal(bel, d["bel%d" % t])
+        bits = dec.decode(rr, d["nit"])
+        tb, ok = dec.checkCrcAndMerge(bits)
+        assert np.array_equal(tb, d["merged%d" % t]) and list(ok) == list(d["cbok%d" % t])
+        assert bool(dec.checkCrc(tb, '24A')) == bool(d["tbok%d" % t])
+        # fused chain with HARQ combining (fp64): same bits, same soft buffer
+        out, cbok, tbok = dec.decodeLLRs(llr, A, d["nit"], harq=hf)
+        assert np.array_equal(out, d["merged%d" % t][:A]) and list(cbok) == list(d["cbok%d" % t])
+        assert bool(tbok) == bool(d["tbok%d" % t]) and np.array_equal(hf.decBuffer, d["decbuf%d" % t])
+        # fp32 kernel == reference algorithm evaluated in fp32 (bit for bit)
+        bel32 = dec32.decode(rr, d["nit"], False, True)
+        obel32 = OC.decode_beliefs(rr.astype(np.float32), bg, d["Zc"], d["iLS"], d["nit"], np.float32)
+        assert np.array_equal(bel32, obel32.astype(np.float64))
+
+
+def test_crc_all_polynomials(ref_cases):
+    _, crc = ref_cases
+    rng = np.random.default_rng(3)
+    for poly in O.CRC_POLYS:
+        assert np.array_equal(ChanCodeBase.getCrc(crc[poly + "/in1"], poly), crc[poly + "/out1"])
+        assert np.array_equal(ChanCodeBase.getCrc(crc[poly + "/in2"], poly), crc[poly + "/out2"])
+        assert np.array_equal(ChanCodeBase.getCrc(np.array([0, 0, 0, 0, 0, 0, 0, 1]), poly), crc[poly + "/one"])
+        for shape in [(1,), (5,), (255,), (256,), (257,), (4, 1000), (2, 8448), (1, 300001)]:
+            b = rng.integers(0, 2, shape).astype(np.int8)
+            got = ChanCodeBase.getCrc(b, poly)
+            assert got.dtype == np.int64 and np.array_equal(got, O.crc_remainder(b, poly))
+            a = ChanCodeBase.appendCrc(b, poly)
+            assert np.array_equal(a, O.crc_attach(b, poly)) and np.all(ChanCodeBase.checkCrc(a, poly))
+            a[..., 0] ^= 1
+            assert not np.any(ChanCodeBase.checkCrc(a, poly))
+    assert isinstance(ChanCodeBase.checkCrc(np.zeros(30, np.int8), '24A'), (bool, np.bool_))
+    assert ChanCodeBase.checkCrc(np.zeros((3, 30), np.int8), '16').shape == (3,)
+    with pytest.raises(KeyError):
+        ChanCodeBase.getCrc(np.zeros(8, np.int8), '32')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+CHAIN_CASES = [
+    (1, 10000, 'QPSK', 449 / 1024, 1, 0), (2, 3000, 'QPSK', 0.3, 1, 0), (1, 8400 * 4, '16QAM', 0.6, 1, 0),
+    (1, 3000, '64QAM', 0.5, 1, 2), (2, 300, 'QPSK', 0.25, 1, 3), (1, 1200, '16QAM', 0.4, 2, 0), (2, 100, 'BPSK', 0.2, 1, 0),
+    (2, 40, 'QPSK', 0.2, 1, 1), (1, 500, '256QAM', 0.7, 1, 0), (1, 20000, '256QAM', 0.8, 4, 1), (2, 3800, '1024QAM', 0.5, 1, 0),
+    (1, 8424 * 3 - 24, '16QAM', 1 / 3, 1, 0), (2, 9000, 'QPSK', 0.2, 1, 0), (2, 12, 'QPSK', 0.2, 1, 0), (1, 30, 'QPSK', 0.34, 1, 0),
+]
+
+
+@pytest.mark.parametrize("prec", ["fp64", "fp32"])
+@pytest.mark.parametrize("bg,A,mod,rate,nl,rv", CHAIN_CASES)
+def test_chain_vs_oracle(bg, A, mod, rate, nl, rv, prec):
+    rng = np.random.default_rng(A * 7 + rv)
+    enc = LdpcEncoder(bg, mod, nl, 0, rate)
+    tb = rng.integers(0, 2, A).astype(np.int8)
+    g = int(np.ceil(A / rate))
+    cbs = enc.doSegmentation(enc.appendCrc(tb, '24A'))
+    ocbs, p = O.segment(O.crc_attach(tb, '24A'), bg)
+    assert np.array_equal(cbs, ocbs)
+    coded = enc.encode(cbs)
+    ocoded = O.encode(ocbs, bg, p['Zc'], p['iLS'])
+    assert np.array_equal(coded, ocoded)
+    rm = enc.rateMatch(coded, g, True, rv)
+    orm = O.rate_match(ocoded, bg, p['Zc'], p['K'], p['F'], g, enc.qm, nl, 0, rv)
+    assert np.array_equal(rm, orm)
+    lst = enc.rateMatch(coded, g, False, rv)
+    assert isinstance(lst, list) and np.array_equal(np.concatenate(lst), orm)
+    with pytest.raises(ValueError):
+        enc.rateMatch(coded, g, True, 4)
+    sigma = 0.7
+    llr = (2 * ((1 - 2.0 * orm) + sigma * rng.standard_normal(len(orm))) / sigma ** 2).astype(np.float32).astype(np.float64)
+    dt = np.float64 if prec == 'fp64' else np.float32
+    dec = LdpcDecoder(bg, mod, nl, 0, precision=prec)
+    h = Harq(rv)
+    rr = dec.recoverRate(llr, A, h)
+    orr, obuf, _ = O.rate_recover(llr, A, bg, enc.qm, nl, 0, rv)
+    assert np.array_equal(rr, orr) and np.array_equal(h.decBuffer, obuf)
+    rr2 = dec.recoverRate(llr * 0.5, A, h)                       # soft combining of a second transmission
+    orr2, obuf2, _ = O.rate_recover(llr * 0.5, A, bg, enc.qm, nl, 0, rv, soft_buffer=obuf)
+    assert np.array_equal(rr2, orr2) and np.array_equal(h.decBuffer, obuf2)
+    for nit in (0, 1, 6):
+        bel = dec.decode(rr, nit, False, True)
+        obel = OC.decode_beliefs(orr, bg, p['Zc'], p['iLS'], nit, dt).astype(np.float64)
+        assert bel.dtype == np.float64 and np.array_equal(bel, obel)
+    bits = dec.decode(rr, 6)
+    obits = (obel[:, :p['K']] < 0).astype(np.int8)
+    assert np.array_equal(bits, obits)
+    assert np.array_equal(dec.decode(rr, 6, True, True), obel[:, :p['K']])
+    tbm, ok = dec.checkCrcAndMerge(bits)
+    otbm, ook = O.check_crc_and_merge(obits, p['K'], p['F'], p['C'])
+    assert np.array_equal(tbm, otbm) and list(ok) == list(ook)
+    x = llr if prec == 'fp64' else llr.astype(np.float32)
+    ftb, fcb, ftbok = dec.decodeLLRs(x, A, 6, harq=Harq(rv))
+    assert np.array_equal(ftb, otbm[:A]) and list(fcb) == list(ook) and bool(ftbok) == bool(O.crc_check(otbm, '24A'))
+    # truncated input: the missing tail counts as zero LLRs (ldpc.py:1402-1403)
+    cut = len(llr) - min(7, len(llr) // 3)
+    assert np.array_equal(dec.recoverRate(llr[:cut], A, Harq(rv)), O.rate_recover(llr[:cut], A, bg, enc.qm, nl, 0, rv)[0])
+
+
+def test_decode_special_values():
+    """+-0.0, huge / infinite LLRs (clipped to 1e10), all-zero input, the +100000 quirk regime."""
+    rng = np.random.default_rng(9)
+    bg, zc, ils = 2, 40, 2
+    cw = O.encode(rng.integers(0, 2, (3, 10 * zc)).astype(np.int8), bg, zc, ils)
+    llr = (1 - 2.0 * cw) * 3 + 2.0 * rng.standard_normal(cw.shape)
+    llr[0, ::7] = -0.0
+    llr[0, 1::11] = 0.0
+    llr[1] = (1 - 2.0 * cw[1]) * 1e20            # noise-free "certain" LLRs: every |t| > 1e5 => the quirk decides min2
+    llr[1, 5] = np.inf
+    llr[1, 6] = -np.inf
+    llr[2] = 0.0
+    for prec, dt in (("fp64", np.float64), ("fp32", np.float32)):
+        dec = LdpcDecoder(bg, 'QPSK', precision=prec)
+        dec.liftingSize, dec.setIndex, dec.codeBlockSize = zc, ils, 10 * zc
+        for nit in (1, 3):
+            got = dec.decode(llr, nit, False, True)
+            want = OC.decode_beliefs(llr.astype(dt), bg, zc, ils, nit, dt).astype(np.float64)
+            assert np.array_equal(got, want)
+
+
+def test_row_skipping_flag_is_exact():
+    """nrldpc_decode with and without NRLDPC_DEC_ALL_ROWS gives identical bits and beliefs on ALL columns."""
+    rng = np.random.default_rng(21)
+    for bg, zc, keep_cols in [(1, 384, 37), (2, 64, 20), (1, 48, 66), (1, 30, 22)]:
+        _, n, k = O.bg_dims(bg)
+        ils = O.set_index_of(zc)
+        C = 5
+        cw = O.encode(rng.integers(0, 2, (C, k * zc)).astype(np.int8), bg, zc, ils)
+        llr = ((1 - 2.0 * cw) * 3 + 2.2 * rng.standard_normal(cw.shape)).astype(np.float32)
+        llr[:, keep_cols * zc - zc // 3:] = 0
+        x = torch.from_numpy(llr).cuda()
+        res = []
+        for flags in (0, _native.DEC_ALL_ROWS):
+            bel = torch.empty((C, n * zc), dtype=torch.float32, device='cuda')
+            bits = torch.empty((C, n * zc), dtype=torch.int8, device='cuda')
+            _native.check(_native.lib().nrldpc_decode(_dev.handle(), bg, zc, _native.F32, _native.F32, _dev.ptr(x), C,
+                                                      (n - 2) * zc, n - 2, 5, flags, n, _dev.ptr(bits), _dev.ptr(bel),
+                                                      None, _dev.stream_ptr()))
+            res.append((bel.cpu().numpy(), bits.cpu().numpy()))
+        want = OC.decode_beliefs(llr, bg, zc, ils, 5, np.float32)
+        assert np.array_equal(res[0][0], want) and np.array_equal(res[1][0], want)
+        assert np.array_equal(res[0][1], (want < 0).astype(np.int8)) and np.array_equal(res[1][1], res[0][1])
+
+
+def test_early_stop_parity_protocol():
+    """Early termination is an extension: the kernel reports the per-block iteration count n, and the block's output
+    must equal the oracle run with numIter = n; a stopped block satisfies every parity check."""
+    rng = np.random.default_rng(33)
+    bg, A, g = 1, 8424 * 2 - 24, 14040 * 2
+    codec = TbBatchCodec(bg, '16QAM', A, g, precision='fp32', earlyStop=True)
+    numTb = 6
+    pl = torch.from_numpy(rng.integers(0, 2, (numTb, A)).astype(np.int8)).cuda()
+    rm = codec.encode(pl)
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(5)
+    llr = qam_awgn_llr(rm, 4, 8.3, generator=gen)
+    out = codec.decode(llr, 12)
+    iters = out["iters"].cpu().numpy().reshape(-1)
+    assert iters.min() >= 1 and iters.max() <= 12 and len(set(iters.tolist())) > 1
+    llr_h = llr.cpu().numpy()
+    tb_h = out["tb"].cpu().numpy()
+    for t in range(numTb):
+        rr, _, p = O.rate_recover(llr_h[t], A, bg, 4, dtype=np.float32)
+        for r in range(2):
+            n_it = int(iters[t * 2 + r])
+            bel = OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, n_it, np.float32)
+            hard = (bel < 0).astype(np.int8)
+            assert np.array_equal(tb_h[t, r * codec.per:(r + 1) * codec.per], hard[0, :codec.per])
+            if n_it < 12:
+                assert O.parity_ok(hard[0], bg, 384, 1)
+                if n_it > 1:   # and it had NOT converged one iteration earlier
+                    prev = (OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, n_it - 1, np.float32) < 0).astype(np.int8)
+                    assert not O.parity_ok(prev[0], bg, 384, 1)
+
+
+@pytest.mark.parametrize("bg,A,mod,rate,numTb", [(2, 500, 'QPSK', 0.3, 23), (1, 600, '16QAM', 0.5, 40), (2, 24, 'QPSK', 0.25, 130),
+                                                  (1, 20000, '64QAM', 0.75, 5), (1, 2000, 'QPSK', 0.4, 9)])
+def test_batched_codec_small_z_multi_cb_per_cta(bg, A, mod, rate, numTb):
+    """Batches of equally configured TBs: several code blocks share a CTA at small Zc, last group partially filled."""
+    rng = np.random.default_rng(A)
+    qm = {'QPSK': 2, '16QAM': 4, '64QAM': 6}[mod]
+    g = int(np.ceil(A / rate / qm)) * qm
+    codec = TbBatchCodec(bg, mod, A, g, precision='fp32')
+    pl = rng.integers(0, 2, (numTb, A)).astype(np.int8)
+    rm = codec.encode(torch.from_numpy(pl).cuda()).cpu().numpy()
+    llr = np.empty(rm.shape, np.float32)
+    for t in range(numTb):
+        orm, p = O.tx_chain(pl[t], bg, g, qm)
+        assert np.array_equal(rm[t, :len(orm)], orm)
+        llr[t] = nr_link.qam_awgn_llr(orm, qm, 3.0 + 10 * np.log10(rate * qm), rng)
+    out = codec.decode(torch.from_numpy(llr).cuda(), 5)
+    tb, cbok, tbok = out["tb"].cpu().numpy(), out["cbOk"].cpu().numpy(), out["tbOk"].cpu().numpy()
+    for t in range(numTb):
+        rr, _, p = O.rate_recover(llr[t], A, bg, qm, dtype=np.float32)
+        hard = (OC.decode_beliefs(rr, bg, p["Zc"], p["iLS"], 5, np.float32)[:, :p["K"]] < 0).astype(np.int8)
+        otb, ocb = O.check_crc_and_merge(hard, p["K"], p["F"], p["C"])
+        assert np.array_equal(tb[t], otb) and list(cbok[t].astype(bool)) == list(ocb)
+        assert bool(tbok[t]) == bool(O.crc_check(otb, '24A'))
+    counters = torch.zeros(8, dtype=torch.int64, device='cuda')
+    codec.accumulate(out, counters, refPayload=torch.from_numpy(pl).cuda())
+    c = counters.cpu().numpy()
+    assert c[0] == numTb * codec.C and c[2] == numTb and c[1] == (cbok == 0).sum() and c[3] == (tbok == 0).sum()
+    assert c[4] == (tb[:, :A] != pl).sum() and c[5] == 5 * numTb * codec.C
+
+
+def test_full_size_config2_properties():
+    """BASELINE configs[1] at full size (1024 code blocks, BG1 Zc=384, 16QAM, R=0.6): size-independent properties
+    (valid code words, encoder linearity, encode -> noise-free recover -> decode round trip, CRC consistency) plus a
+    64-block sample through the oracle bit for bit."""
+    A, g, numTb = 8424 * 16 - 24, 14040 * 16, 64
+    codec = TbBatchCodec(1, '16QAM', A, g, precision='fp32')
+    gen = torch.Generator(device='cuda')
+    gen.manual_seed(20261017)
+    pa = torch.randint(0, 2, (numTb, A), dtype=torch.int8, device='cuda', generator=gen)
+    pb = torch.randint(0, 2, (numTb, A), dtype=torch.int8, device='cuda', generator=gen)
+    L, h, s = _native.lib(), _dev.handle(), _dev.stream_ptr()
+
+    def coded_full(pl):
+        tb = torch.empty((numTb, A + 24), dtype=torch.int8, device='cuda')
+        _native.check(L.nrldpc_crc_attach(h, _dev.ptr(pl), numTb, A, A, 3, _dev.ptr(tb), s))
+        cbs = torch.empty((numTb * 16, 8448), dtype=torch.int8, device='cuda')
+        _native.check(L.nrldpc_segment(h, codec.cfg, _dev.ptr(tb), numTb, A + 24, A + 24, _dev.ptr(cbs), s))
+        full = torch.empty((numTb * 16, 68 * 384), dtype=torch.int8, device='cuda')
+        _native.check(L.nrldpc_encode(h, 1, 384, _dev.ptr(cbs), numTb * 16, _dev.ptr(full), 0, s))
+        return cbs, full
+    cbs_a, full_a = coded_full(pa)
+    ok = torch.empty((numTb * 16,), dtype=torch.uint8, device='cuda')
+    _native.check(L.nrldpc_parity_check(h, 1, 384, _dev.ptr(full_a), numTb * 16, _dev.ptr(ok), s))
+    assert int(ok.sum()) == numTb * 16                                  # every encoded block is a code word
+    assert torch.equal(full_a[:, :8448], cbs_a)                         # systematic
+    # linearity over GF(2): enc(a ^ b) == enc(a) ^ enc(b) on raw code blocks
+    cbs_b = torch.randint(0, 2, cbs_a.shape, dtype=torch.int8, device='cuda', generator=gen)
+    ea, eb, eab = (torch.empty((numTb * 16, 66 * 384), dtype=torch.int8, device='cuda') for _ in range(3))
+    for src, dst in ((cbs_a, ea), (cbs_b, eb), (cbs_a ^ cbs_b, eab)):
+        _native.check(L.nrldpc_encode(h, 1, 384, _dev.ptr(src.contiguous()), numTb * 16, _dev.ptr(dst), 1, s))
+    assert torch.equal(ea ^ eb, eab)
+    # round trip without noise and with noise at 9 dB
+    rm = codec.encode(pa)
+    for llr in ((1 - 2 * rm.to(torch.float32)) * 4, qam_awgn_llr(rm, 4, 9.0, generator=gen)):
+        out = codec.decode(llr.contiguous(), 8)
+        assert torch.equal(out["tb"][:, :A], pa) and int(out["tbOk"].sum()) == numTb and int(out["cbOk"].sum()) == numTb * 16
+    # oracle sample: first 4 TBs = 64 code blocks, fp32 bit for bit
+    llr_h = llr[:4].cpu().numpy()
+    tb_h = out["tb"][:4].cpu().numpy()
+    for t in range(4):
+        rr, _, p = O.rate_recover(llr_h[t], A, 1, 4, dtype=np.float32)
+        hard = (OC.decode_beliefs(rr, 1, 384, 1, 8, np.float32)[:, :8448] < 0).astype(np.int8)
+        otb, ocb = O.check_crc_and_merge(hard, 8448, 0, 16)
+        assert np.array_equal(tb_h[t], otb) and all(ocb)
+
+
+def test_wraparound_and_lbrm_recover():
+    """E > Ncb (repetition: several LLRs accumulate into one buffer position, in stream order) and nRef-limited buffers."""
+    rng = np.random.default_rng(2)
+    for bg, A, mod, g, nref in [(2, 100, 'BPSK', 5000, 0), (2, 60, 'QPSK', 7000, 0), (1, 2400, 'QPSK', 4800, 7392), (1, 2400, 'QPSK', 4800, 5000),
+                                 (2, 1000, '16QAM', 40000, 0)]:
+        qm = O.MOD_ORDER[mod]
+        llr = rng.standard_normal(g) * 3
+        for prec_rv in (0, 2):
+            dec = LdpcDecoder(bg, mod, 1, nref)
+            h = Harq(prec_rv)
+            got = dec.recoverRate(llr, A, h)
+            want, buf, _ = O.rate_recover(llr, A, bg, qm, 1, nref, prec_rv)
+            assert np.array_equal(got, want) and np.array_equal(h.decBuffer, buf)
+
+
+def test_error_behaviour_on_gpu():
+    dec = LdpcDecoder(1, 'QPSK')
+    h = Harq()
+    h.decBuffer = np.zeros((3, 7))
+    with pytest.raises(AssertionError):
+        dec.recoverRate(np.zeros(22808), 10000, h)
+    enc = LdpcEncoder(1, 'QPSK')
+    enc.initialize(10024)
+    with pytest.raises(AssertionError):
+        enc.encode(np.zeros((2, 100), np.int8))
+    p = ctypes.c_void_p()
+    assert _native.lib().nrldpc_create(99, ctypes.byref(p)) == _native.ERR_ARG
+    with pytest.raises(ValueError):
+        _native.check(_native.lib().nrldpc_decode(_dev.handle(), 1, 100, 0, 0, None, 1, 100, 66, 1, 0, 22, None, None, None, None))
