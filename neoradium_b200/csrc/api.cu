@@ -105,6 +105,8 @@ extern "C" int nrldpc_create(int device, nrldpc_handle** out)
     h->smemPerSM = (int)prop.sharedMemPerMultiprocessor;
     const char* occ = getenv("NRLDPC_DEC_OCC");
     h->decOcc = occ ? atoi(occ) : 0;
+    const char* nt = getenv("NRLDPC_NO_TMEM");
+    h->noTmem = nt ? atoi(nt) : 0;
     e = cudaMalloc(&h->workCounter, 16 * sizeof(unsigned int));
     if (e != cudaSuccess) { free(h); nr_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return NRLDPC_ERR_CUDA; }
     cudaMemset(h->workCounter, 0, 16 * sizeof(unsigned int));

@@ -23,9 +23,23 @@
 // (no FMA contraction), operation order t = r - old; new = (mag*sign)*0.75; r = t + new, sign(+-0) = +, first-index
 // argmin, the "+100000" second-minimum quirk, clip to +-1e10.  -0.0 inputs are canonicalised to +0.0 at load, which
 // makes the raw sign bit equal to (t < 0) for every t the recursion can produce.
+#include <string.h>
+
 #include "nrldpc_internal.cuh"
 
+#ifndef NR_DEC_MIN_CTAS
+#define NR_DEC_MIN_CTAS 2   // fp32: cap registers at 80 so that two 384-thread CTAs share an SM
+#endif
+
 namespace {
+
+// decoder view of the lifted graph: byte offsets instead of (column, shift), see process_row
+struct __align__(16) NrDecGraph {
+    int P, ncols, ksys, ncore, Z, pad[3];
+    uint16_t rowEdge0[NR_MAX_ROWS + 2];
+    uint2 tab[NR_MAX_EDGES];   // x = (col*Z + shift)*sizeof(T), y = (col*Z + Z)*sizeof(T)
+};
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // exact arithmetic helpers
@@ -45,6 +59,13 @@ struct FP<float> {
         return __uint_as_float(__float_as_uint(mag) ^ (bit << 31));
     }
     static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+    static __device__ __forceinline__ uint32_t hibits(float a) { return __float_as_uint(a); }
+    static __device__ __forceinline__ void opaque(float& a) { asm volatile("" : "+f"(a)); }
+    // mag with its sign flipped when bit 31 of `w` is set (the other bits of w are ignored)
+    static __device__ __forceinline__ float flipbits(float mag, uint32_t w)
+    {
+        return __uint_as_float(__float_as_uint(mag) ^ (w & 0x80000000u));
+    }
 };
 template <>
 struct FP<double> {
@@ -59,6 +80,12 @@ struct FP<double> {
         return __hiloint2double(__double2hiint(mag) ^ (int)(bit << 31), __double2loint(mag));
     }
     static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+    static __device__ __forceinline__ uint32_t hibits(double a) { return (uint32_t)__double2hiint(a); }
+    static __device__ __forceinline__ void opaque(double& a) { asm volatile("" : "+d"(a)); }
+    static __device__ __forceinline__ double flipbits(double mag, uint32_t w)
+    {
+        return __hiloint2double(__double2hiint(mag) ^ (int)(w & 0x80000000u), __double2loint(mag));
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -71,12 +98,15 @@ struct DecArgs {
     int numIter;
     int flags;
     int numRows;        // rows scheduled (>= 4); rows >= numRows have all-zero extension LLRs
-    int smemRows;       // rows whose state planes live in shared memory; the rest go to `scratch`
+    int tmemRows;       // rows [0, tmemRows): state in Tensor Memory (ONE_CB kernels only)
+    int tmemCols;       // TMEM columns to allocate (power of two >= 32), 0 = none
+    int smemRows;       // next smemRows rows: state planes in shared memory; the rest go to `scratch`
     int outCols;        // columns written to bits / beliefs
     // mode A: rate-recovered input
     const void* llr;
     long long llrStride;
     int inCols;
+    int inF64;          // element type of `llr` (compute type T is the kernel's template parameter)
     // mode B: fused rate recovery (rm != 0)
     int rm;
     int K, F, C, qm, ncb, k0, E0, nShort, fStep;   // per-TB split: first nShort blocks have E0, the rest E0+fStep
@@ -101,34 +131,92 @@ struct DecArgs {
 enum { PL_M1 = 0, PL_M2 = 1, PL_SW = 2, PL_REXT = 3, NPLANES = 4 };
 
 template <typename T>
-struct RowAccess {
-    T* base;   // plane 0 of this row for this thread (already offset by tid)
-    int nT;
-    __device__ __forceinline__ T ld(int plane) const { return base[(size_t)plane * nT]; }
-    __device__ __forceinline__ void st(int plane, T v) const { base[(size_t)plane * nT] = v; }
-    __device__ __forceinline__ uint32_t ldsw() const { return *reinterpret_cast<const uint32_t*>(base + (size_t)PL_SW * nT); }
-    __device__ __forceinline__ void stsw(uint32_t v) const { *reinterpret_cast<uint32_t*>(base + (size_t)PL_SW * nT) = v; }
+struct RowState {   // register copy of one check's state
+    T m1s, m2s, rext;
+    uint32_t sw;
 };
+
+// plane access through a pointer whose address space (shared / global) is known at the call site
+template <typename T>
+__device__ __forceinline__ void load_state(RowState<T>& st, const T* base, int nT)
+{
+    st.m1s = base[(size_t)PL_M1 * nT];
+    st.m2s = base[(size_t)PL_M2 * nT];
+    st.sw = *reinterpret_cast<const uint32_t*>(base + (size_t)PL_SW * nT);
+    st.rext = base[(size_t)PL_REXT * nT];
+}
+template <typename T>
+__device__ __forceinline__ void store_state(const RowState<T>& st, T* base, int nT)
+{
+    base[(size_t)PL_M1 * nT] = st.m1s;
+    base[(size_t)PL_M2 * nT] = st.m2s;
+    *reinterpret_cast<uint32_t*>(base + (size_t)PL_SW * nT) = st.sw;
+    base[(size_t)PL_REXT * nT] = st.rext;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor Memory as thread-private state storage (B200: 256 KB / SM next to the 227 KB of shared memory).
+// The per-check state is touched by exactly one thread, once per iteration, and never needs a barrier -- it only
+// needs CAPACITY.  TMEM is addressed as 128 lanes x 512 columns of 32 bits; with the 32x32b access shape a warp
+// reads/writes, for each of its 32 threads, consecutive columns of the lane (warp % 4) * 32 + laneid.  Row slot s of
+// warp w therefore lives in columns base + (s * warpsPerQuad + w / 4) * RW .. + RW-1 of the warp's lane quadrant,
+// RW = 4 words (fp32 state) or 8 (fp64).  This frees ~100 KB of shared memory per code block, which is what lets
+// two BG1/Zc=384 code blocks share one SM.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld(RowState<float>& st, uint32_t taddr)
+{
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    st.m1s = __uint_as_float(a); st.m2s = __uint_as_float(b); st.sw = c; st.rext = __uint_as_float(d);
+}
+__device__ __forceinline__ void tmem_st(const RowState<float>& st, uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(st.m1s)),
+                 "r"(__float_as_uint(st.m2s)), "r"(st.sw), "r"(__float_as_uint(st.rext)) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld(RowState<double>& st, uint32_t taddr)
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    st.m1s = __hiloint2double((int)r[1], (int)r[0]);
+    st.m2s = __hiloint2double((int)r[3], (int)r[2]);
+    st.rext = __hiloint2double((int)r[5], (int)r[4]);
+    st.sw = r[6];
+}
+__device__ __forceinline__ void tmem_st(const RowState<double>& st, uint32_t taddr)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+                 "r"((uint32_t)__double2loint(st.m1s)), "r"((uint32_t)__double2hiint(st.m1s)),
+                 "r"((uint32_t)__double2loint(st.m2s)), "r"((uint32_t)__double2hiint(st.m2s)),
+                 "r"((uint32_t)__double2loint(st.rext)), "r"((uint32_t)__double2hiint(st.rext)), "r"(st.sw), "r"(0u) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // one layer for one lifted check.  D = row degree, EXT = last edge is the thread-private extension column.
-// sw layout: bits 0..18 sign of the stored message per edge, bits 24..28 argmin edge.
+// sw layout: bit (D-1-j) = sign of the stored message of edge j, bits 24..28 = argmin edge.
+//
+// Instruction budget per edge (the kernel is bound by the half-rate ALU pipe):
+//   address  : u = mB + tab.x; if (u >= tab.y) u -= ZB        (tab = byte offsets precomputed on the host)
+//   gather   : LDS
+//   old msg  : (j == oldIdx ? m2 : m1) ^ (sign bit moved to bit 31), FADD
+//   signs    : one funnel shift collects the sign bit of t
+//   two-min  : compare, 2 selects, 1 min, 1 index select
+//   new msg  : (j == idx ? m2' : m1') ^ (t & 0x80000000) with the parity pre-applied to m1', m2';  FADD;  STS
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int D, bool EXT, bool FIRST, bool SMEM_STATE>
-__device__ __forceinline__ void process_row(const NrGraph& g, int e0, T* __restrict__ rcb, int m, int Z,
-                                            const RowAccess<T>& st)
+template <typename T, int D, bool EXT>
+__device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t mB,
+                                            uint32_t ZB, RowState<T>& st)
 {
     T t[D];
-    int addr[D];
-    T m1s = (T)0, m2s = (T)0;
-    uint32_t sw = 0;
-    int oldIdx = 0;
-    if (!FIRST) {
-        m1s = st.ld(PL_M1);
-        m2s = st.ld(PL_M2);
-        sw = st.ldsw();
-        oldIdx = (int)(sw >> 24);
-    }
+    uint32_t off[D];
+    T m1s = st.m1s, m2s = st.m2s;
+    const uint32_t sw = st.sw;
+    const int oldIdx = (int)(sw >> 24);
     T min1 = (T)0, min2 = FP<T>::inf();
     int idx = 0;
     uint32_t nsw = 0;
@@ -136,23 +224,21 @@ __device__ __forceinline__ void process_row(const NrGraph& g, int e0, T* __restr
     for (int j = 0; j < D; j++) {
         T rv;
         if (EXT && j == D - 1) {
-            rv = st.ld(PL_REXT);
-            addr[j] = 0;
+            rv = st.rext;
+            off[j] = 0;
         } else {
-            const uint32_t ew = g.edge[e0 + j];
-            int p = m + (int)(ew & 0xffffu);
-            p = (p >= Z) ? p - Z : p;
-            addr[j] = (int)(ew >> 16) * Z + p;
-            rv = rcb[addr[j]];
+            const uint2 tb = g.tab[e0 + j];
+            uint32_t u = mB + tb.x;
+            u = (u >= tb.y) ? u - ZB : u;
+            off[j] = u;
+            rv = *reinterpret_cast<const T*>(rb + u);
         }
-        if (FIRST) {
-            t[j] = rv;   // old message is +0: r - 0 == r exactly
-        } else {
+        {   // in the first iteration the state is all zero: r - (+0) == r exactly
             const T mag = (j == oldIdx) ? m2s : m1s;
-            t[j] = FP<T>::sub(rv, FP<T>::flip(mag, (sw >> j) & 1u));
+            t[j] = FP<T>::sub(rv, FP<T>::flipbits(mag, sw << (31 - (D - 1 - j))));
         }
         const T a = FP<T>::abs(t[j]);
-        nsw |= FP<T>::sign(t[j]) << j;
+        nsw = __funnelshift_l(FP<T>::hibits(t[j]), nsw, 1);   // (nsw << 1) | sign(t_j)
         if (j == 0) {
             min1 = a;
         } else {
@@ -164,50 +250,64 @@ __device__ __forceinline__ void process_row(const NrGraph& g, int e0, T* __restr
     }
     // the reference bumps the signed minimum by 1e5 and takes |.| before searching the second minimum (ldpc.py:1563)
     {
-        const T tq = FP<T>::flip(min1, (nsw >> idx) & 1u);
+        const T tq = FP<T>::flip(min1, (nsw >> (D - 1 - idx)) & 1u);
         min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(tq, (T)100000)));
     }
     const uint32_t par = __popc(nsw) & 1u;
     const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;   // sign of new message j = sign_j * parity
     m1s = FP<T>::mul(min1, (T)0.75);
     m2s = FP<T>::mul(min2, (T)0.75);
+    T m1p = FP<T>::flip(m1s, par), m2p = FP<T>::flip(m2s, par);
+    FP<T>::opaque(m1p);   // keep the parity folded into the two candidates instead of one extra XOR per edge
+    FP<T>::opaque(m2p);
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const T mag = (j == idx) ? m2s : m1s;
-        const T nv = FP<T>::add(t[j], FP<T>::flip(mag, (msw >> j) & 1u));
+        const T mag = (j == idx) ? m2p : m1p;
+        const T nv = FP<T>::add(t[j], FP<T>::flipbits(mag, FP<T>::hibits(t[j])));
         if (EXT && j == D - 1)
-            st.st(PL_REXT, nv);
+            st.rext = nv;
         else
-            rcb[addr[j]] = nv;
+            *reinterpret_cast<T*>(rb + off[j]) = nv;
     }
-    st.st(PL_M1, m1s);
-    st.st(PL_M2, m2s);
-    st.stsw(msw | ((uint32_t)idx << 24));
+    st.m1s = m1s;
+    st.m2s = m2s;
+    st.sw = msw | ((uint32_t)idx << 24);
 }
 
-template <typename T, bool FIRST, bool SMEM_STATE>
-__device__ __forceinline__ void dispatch_row(const NrGraph& g, int row, T* rcb, int m, int Z, const RowAccess<T>& st)
+template <typename T>
+__device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t mB, uint32_t ZB,
+                                             RowState<T>& st)
 {
     const int e0 = g.rowEdge0[row];
     const int deg = g.rowEdge0[row + 1] - e0;
     if (row >= 4) {
         switch (deg) {
-            case 3: process_row<T, 3, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 4: process_row<T, 4, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 5: process_row<T, 5, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 6: process_row<T, 6, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 7: process_row<T, 7, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 8: process_row<T, 8, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 9: process_row<T, 9, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            default: process_row<T, 10, true, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 3: process_row<T, 3, true>(g, e0, rb, mB, ZB, st); break;
+            case 4: process_row<T, 4, true>(g, e0, rb, mB, ZB, st); break;
+            case 5: process_row<T, 5, true>(g, e0, rb, mB, ZB, st); break;
+            case 6: process_row<T, 6, true>(g, e0, rb, mB, ZB, st); break;
+            case 7: process_row<T, 7, true>(g, e0, rb, mB, ZB, st); break;
+            case 8: process_row<T, 8, true>(g, e0, rb, mB, ZB, st); break;
+            case 9: process_row<T, 9, true>(g, e0, rb, mB, ZB, st); break;
+            default: process_row<T, 10, true>(g, e0, rb, mB, ZB, st); break;
         }
     } else {
         switch (deg) {
-            case 8: process_row<T, 8, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            case 10: process_row<T, 10, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
-            default: process_row<T, 19, false, FIRST, SMEM_STATE>(g, e0, rcb, m, Z, st); break;
+            case 8: process_row<T, 8, false>(g, e0, rb, mB, ZB, st); break;
+            case 10: process_row<T, 10, false>(g, e0, rb, mB, ZB, st); break;
+            default: process_row<T, 19, false>(g, e0, rb, mB, ZB, st); break;
         }
     }
+}
+
+// posterior addressed by edge `e` for lifted index byte offset mB
+template <typename T>
+__device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t mB, uint32_t ZB)
+{
+    const uint2 tb = g.tab[e];
+    uint32_t u = mB + tb.x;
+    u = (u >= tb.y) ? u - ZB : u;
+    return *reinterpret_cast<const T*>(rb + u);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -230,12 +330,13 @@ __device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b, uint32_t p
 }
 
 // CRC remainder of `len` hard-decision bits of one code block, cooperatively by its Z threads.
-// bit i lives at rcb[i] (posterior < 0).  The message is right-aligned in Z chunks of B bits (leading zeros do not
-// change a zero-initialised CRC), per-thread remainders are merged pairwise: rem = left * x^(span) + right.
-// `tree` is per-CB scratch of >= nextPow2(Z) words.  Every thread of the CTA must call this (barriers inside).
+// Bit i is the sign of posterior i of the block (core columns are contiguous in shared memory).  The message is
+// right-aligned in Z chunks of B bits (leading zeros do not change a zero-initialised CRC); per-thread remainders are
+// merged pairwise, rem = left * x^(B*span) + right, with the factors x^(B*2^l) mod g precomputed in fac[].
+// `tree` is per-block scratch of P2 = nextPow2(Z) words.  Every thread of the CTA must call this (barriers inside).
 template <typename T>
-__device__ uint32_t cb_crc(const T* rcb, int len, int Z, int P2, int m, bool active, uint32_t* tree, uint32_t poly,
-                           int c)
+__device__ uint32_t cb_crc(const T* rcb, int len, int Z, int P2, int m, bool active, uint32_t* tree,
+                           const uint32_t* fac, uint32_t poly, int c)
 {
     const int B = (len + Z - 1) / Z;
     const int lead = B * Z - len;
@@ -252,47 +353,143 @@ __device__ uint32_t cb_crc(const T* rcb, int len, int Z, int P2, int m, bool act
         tree[(P2 - Z) + m] = rem;
         if (m < P2 - Z) tree[m] = 0;   // virtual leading chunks
     }
-    uint32_t f = 1;   // x^B mod g
-    for (int b = 0; b < B; b++) f = gf_shift1(f, poly, c);
     __syncthreads();
-    for (int span = 1; span < P2; span <<= 1) {
-        // worker w merges the pair of spans ending at right = (w+1)*2*span-1:  rem = left * x^(B*span) + right
+    int lvl = 0;
+    for (int span = 1; span < P2; span <<= 1, lvl++) {
         const int right = (m + 1) * 2 * span - 1;
-        if (active && right < P2) tree[right] = gf_mulmod(tree[right - span], f, poly, c) ^ tree[right];
-        f = gf_mulmod(f, f, poly, c);
+        if (active && right < P2) tree[right] = gf_mulmod(tree[right - span], fac[lvl], poly, c) ^ tree[right];
         __syncthreads();
     }
     return active ? tree[P2 - 1] : 0u;
 }
 
+// fac[l] = x^(B * 2^l) mod g for l = 0..nl-1, written by the first nl threads
+__device__ __forceinline__ void crc_factors(uint32_t* fac, int len, int Z, int P2, uint32_t poly, int c, int tid)
+{
+    const int B = (len + Z - 1) / Z;
+    int nl = 0;
+    for (int span = 1; span < P2; span <<= 1) nl++;
+    if (tid < nl) {
+        uint32_t f = 1;
+        for (int b = 0; b < B; b++) f = gf_shift1(f, poly, c);
+        for (int l = 0; l < tid; l++) f = gf_mulmod(f, f, poly, c);
+        fac[tid] = f;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// the kernel
+// three-tier state storage: rows [0, tmemRows) in Tensor Memory (ONE_CB kernels), the next smemRows rows in shared
+// memory planes, the rest in the per-CTA global scratch (stays in L2).  All branches are on the (uniform) row index.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, typename TIn>
-__global__ void __launch_bounds__(384, 1)
-    nr_decode_kernel(const __grid_constant__ NrGraph g, const __grid_constant__ DecArgs a)
+template <typename T, bool ONE_CB>
+struct StateStore {
+    uint32_t tbase;     // this thread's TMEM address of row slot 0 (lane quadrant and warp column offset folded in)
+    uint32_t tstride;   // TMEM columns per row slot
+    T* sS;              // shared planes, already offset by tid
+    T* sG;              // global planes, already offset by tid
+    int tmemRows, smemRows, nT;
+    __device__ __forceinline__ void load(int row, RowState<T>& st) const
+    {
+        if (ONE_CB && row < tmemRows)
+            tmem_ld(st, tbase + (uint32_t)row * tstride);
+        else if (row < tmemRows + smemRows)
+            load_state(st, sS + (size_t)(row - tmemRows) * NPLANES * nT, nT);
+        else
+            load_state(st, sG + (size_t)(row - tmemRows - smemRows) * NPLANES * nT, nT);
+    }
+    __device__ __forceinline__ void store(int row, const RowState<T>& st) const
+    {
+        if (ONE_CB && row < tmemRows)
+            tmem_st(st, tbase + (uint32_t)row * tstride);
+        else if (row < tmemRows + smemRows)
+            store_state(st, sS + (size_t)(row - tmemRows) * NPLANES * nT, nT);
+        else
+            store_state(st, sG + (size_t)(row - tmemRows - smemRows) * NPLANES * nT, nT);
+    }
+};
+
+// one input LLR, widened / narrowed to the compute type
+template <typename T>
+__device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
+{
+    return f64 ? (T) reinterpret_cast<const double*>(p)[i] : (T) reinterpret_cast<const float*>(p)[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the kernel.  ONE_CB: exactly one code block per CTA and blockDim.x == Z (Z a multiple of 32): no thread is ever
+// idle, so the row bodies run in convergent code and the (column, shift) table is read through the uniform datapath.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, bool ONE_CB>
+__global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
+    nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int Z = g.Z;
     const int ncore = g.ncore;
     const int nT = blockDim.x;
     const int tid = threadIdx.x;
-    const int cbl = tid / Z;            // local code block
-    const int m = tid - cbl * Z;        // lifted check / position
-    const bool lane_ok = cbl < a.cbPerCta;
+    const int cbl = ONE_CB ? 0 : tid / Z;            // local code block
+    const int m = ONE_CB ? tid : tid - cbl * Z;      // lifted check / position
+    const bool lane_ok = ONE_CB ? true : (cbl < a.cbPerCta);
+    const int cbPerCta = ONE_CB ? 1 : a.cbPerCta;
 
     T* rs = reinterpret_cast<T*>(smemRaw);                                   // [cbPerCta][ncore][Z]
-    T* stateS = rs + (size_t)a.cbPerCta * ncore * Z;                         // [smemRows][NPLANES][nT]
-    uint32_t* misc = reinterpret_cast<uint32_t*>(stateS + (size_t)a.smemRows * NPLANES * nT);   // flags + crc tree
-    T* stateG = reinterpret_cast<T*>(a.scratch) + (size_t)blockIdx.x * (size_t)(a.numRows - a.smemRows) * NPLANES * nT;
+    T* stateS = rs + (size_t)cbPerCta * ncore * Z;                           // [smemRows][NPLANES][nT]
+    uint32_t* misc = reinterpret_cast<uint32_t*>(stateS + (size_t)a.smemRows * NPLANES * nT);
+    // misc: [0, flagsLen) per-block flags | 32 words CRC factors (2 x 16) | per-block CRC trees
+    const int flagsLen = (cbPerCta + 31) & ~31;
+    uint32_t* fac = misc + flagsLen;
+    int P2 = 1;
+    while (P2 < Z) P2 <<= 1;
+    uint32_t* tree = misc + flagsLen + 32 + (size_t)cbl * P2;
+    const int globRows = a.numRows - a.tmemRows - a.smemRows;
+    T* stateG = reinterpret_cast<T*>(a.scratch) + (size_t)blockIdx.x * (size_t)globRows * NPLANES * nT;
     T* rcb = rs + (size_t)cbl * ncore * Z;
+    // Tensor Memory for the thread-private row state (see tmem_ld above)
+    __shared__ uint32_t tmemBaseSh;
+    const bool useTmem = ONE_CB && a.tmemCols > 0;
+    if (useTmem) {
+        if (tid < 32) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmemBaseSh);
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"((uint32_t)a.tmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    StateStore<T, ONE_CB> store;
+    {
+        const int warp = tid >> 5;
+        const uint32_t RW = sizeof(T) == 4 ? 4u : 8u;
+        const uint32_t wpq = (uint32_t)((nT >> 5) + 3) >> 2;              // warps per lane quadrant
+        store.tstride = wpq * RW;
+        store.tbase = useTmem ? (tmemBaseSh + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * RW) : 0u;   // lane (warp%4)*32 in bits 31..16
+        store.sS = stateS + tid;
+        store.sG = stateG + tid;
+        store.tmemRows = ONE_CB ? a.tmemRows : 0;
+        store.smemRows = a.smemRows;
+        store.nT = nT;
+    }
+    char* rb = reinterpret_cast<char*>(rcb);
+    const uint32_t mB = (uint32_t)m * (uint32_t)sizeof(T);
+    const uint32_t ZB = (uint32_t)Z * (uint32_t)sizeof(T);
     const int ksys = g.ksys;
-    const int N = (g.ncols - 2) * Z;
 
-    const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
+    const bool wantCrc = a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA);
+    const int Lk = a.K - a.F;                       // code block without fillers
+    const int per = (a.C > 1) ? Lk - 24 : Lk;       // payload copied into the merged transport block
+    const NrCrcPoly polyCb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
+    const NrCrcPoly polyA = nr_crc_poly(NRLDPC_CRC24A);
+    if (wantCrc) {
+        crc_factors(fac, Lk, Z, P2, polyCb.poly, polyCb.len, tid);
+        if (a.C > 1) crc_factors(fac + 16, per, Z, P2, polyA.poly, polyA.len, tid);
+    }
+
+    const long long numGroups = (a.numCb + cbPerCta - 1) / cbPerCta;
     for (long long grp = blockIdx.x; grp < numGroups; grp += gridDim.x) {
-        const long long cb = grp * a.cbPerCta + cbl;
-        const bool active = lane_ok && cb < a.numCb;
+        const long long cb = grp * cbPerCta + cbl;
+        const bool active = ONE_CB ? true : (lane_ok && cb < a.numCb);
 
         // -------------------------------------------------------------------------------------------------------
         // load phase: column block `col` (un-punctured index), position m.  Punctured columns 0,1 start at 0.
@@ -300,29 +497,28 @@ __global__ void __launch_bounds__(384, 1)
         if (active) {
             rcb[m] = (T)0;
             rcb[Z + m] = (T)0;
-            const int lastCol = (a.numRows >= 4) ? (ksys + a.numRows) : ncore;   // exclusive
-            // fused rate-recovery parameters of this code block
+            const int lastCol = ksys + a.numRows;   // exclusive; numRows >= 4
             int E = 0, L = 0, sysLen = 0, Eq = 1;
-            const TIn* x = nullptr;
+            long long xBase = 0, xAvail = 0;
             T* sb = nullptr;
-            long long xAvail = 0;
             if (a.rm) {
                 const long long tb = cb / a.C;
                 const int r = (int)(cb - tb * a.C);
                 E = a.E0 + (r >= a.nShort ? a.fStep : 0);
                 const long long off = (long long)r * a.E0 + (long long)(r > a.nShort ? (r - a.nShort) : 0) * a.fStep;
-                x = reinterpret_cast<const TIn*>(a.llr) + tb * a.llrStride + off;
+                xBase = tb * a.llrStride + off;
                 xAvail = a.llrLen - off;   // LLRs actually present for this block (rest are zeros, ldpc.py:1402)
                 L = a.ncb - a.F;
                 sysLen = a.K - a.F - 2 * Z;
                 Eq = E / a.qm;
                 if (a.softBuf) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
             }
-            for (int col = 2; col < lastCol; col++) {
+            const int colEnd = (a.rm && sb) ? g.ncols : lastCol;   // a soft buffer is combined over its whole length
+            for (int col = 2; col < colEnd; col++) {
                 const int n = (col - 2) * Z + m;   // index in the punctured coded block
                 T v = (T)0;
                 if (!a.rm) {
-                    if (col - 2 < a.inCols) v = (T)reinterpret_cast<const TIn*>(a.llr)[cb * a.llrStride + n];
+                    if (col - 2 < a.inCols) v = load_llr<T>(a.llr, cb * a.llrStride + n, a.inF64);
                 } else if (n < a.ncb) {
                     if (n >= sysLen && n < sysLen + a.F) {
                         v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
@@ -332,43 +528,31 @@ __global__ void __launch_bounds__(384, 1)
                         int i = q - a.k0;
                         if (i < 0) i += L;
                         for (; i < E; i += L) {       // one term per wrap, ascending => the reference's += order
-                            const int s = i % Eq, b = i / Eq;   // de-interleave: stream index s*qm + b
-                            const long long xi = (long long)s * a.qm + b;
-                            const T xv = (xi < xAvail) ? (T)x[xi] : (T)0;
+                            const int b = i / Eq, sI = i - b * Eq;   // de-interleave: stream index s*qm + b
+                            const long long xi = (long long)sI * a.qm + b;
+                            const T xv = (xi < xAvail) ? load_llr<T>(a.llr, xBase + xi, a.inF64) : (T)0;
                             acc = FP<T>::add(acc, xv);
                         }
                         if (sb) sb[q] = acc;
                         v = acc;
                     }
                 }
+                if (col >= lastCol) continue;           // beyond the scheduled rows: only the soft buffer is updated
                 v = (v > (T)1e10) ? (T)1e10 : v;        // np.clip(., -1e10, 1e10), ldpc.py:1536
                 v = (v < (T)-1e10) ? (T)-1e10 : v;
                 v = FP<T>::add(v, (T)0);                 // -0.0 -> +0.0 (see header)
                 if (col < ncore) {
                     rcb[col * Z + m] = v;
                 } else {
-                    const int row = col - ksys;
-                    T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
-                                                 : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
-                    base[(size_t)PL_REXT * nT] = v;
+                    RowState<T> st0;   // messages start at +0 (ldpc.py:1543), posterior of the extension column = its LLR
+                    st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = v;
+                    store.store(col - ksys, st0);
                 }
             }
-            if (a.rm && sb) {
-                // soft-buffer positions beyond the scheduled rows still have to be combined (HARQ keeps them)
-                for (int col = lastCol; col < g.ncols; col++) {
-                    const int n = (col - 2) * Z + m;
-                    if (n >= a.ncb || (n >= sysLen && n < sysLen + a.F)) continue;
-                    const int q = (n < sysLen) ? n : n - a.F;
-                    T acc = sb[q];
-                    int i = q - a.k0;
-                    if (i < 0) i += L;
-                    for (; i < E; i += L) {
-                        const int s = i % Eq, b = i / Eq;
-                        const long long xi = (long long)s * a.qm + b;
-                        acc = FP<T>::add(acc, (xi < xAvail) ? (T)x[xi] : (T)0);
-                    }
-                    sb[q] = acc;
-                }
+            for (int row = 0; row < 4; row++) {
+                RowState<T> st0;
+                st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = (T)0;
+                store.store(row, st0);
             }
         }
         __syncthreads();
@@ -380,26 +564,17 @@ __global__ void __launch_bounds__(384, 1)
         bool cbDone = false;
         for (int it = 0; it < a.numIter; it++) {
             for (int row = 0; row < a.numRows; row++) {
-                if (active && !cbDone) {
-                    if (row < a.smemRows) {
-                        RowAccess<T> st{stateS + (size_t)row * NPLANES * nT + tid, nT};
-                        if (it == 0)
-                            dispatch_row<T, true, true>(g, row, rcb, m, Z, st);
-                        else
-                            dispatch_row<T, false, true>(g, row, rcb, m, Z, st);
-                    } else {
-                        RowAccess<T> st{stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid, nT};
-                        if (it == 0)
-                            dispatch_row<T, true, false>(g, row, rcb, m, Z, st);
-                        else
-                            dispatch_row<T, false, false>(g, row, rcb, m, Z, st);
-                    }
+                if (ONE_CB || (active && !cbDone)) {
+                    RowState<T> st;
+                    store.load(row, st);
+                    dispatch_row<T>(g, row, rb, mB, ZB, st);
+                    store.store(row, st);
                 }
                 __syncthreads();
             }
             if (!cbDone) itersDone = it + 1;
             if (a.flags & NRLDPC_DEC_EARLY_STOP) {
-                // syndrome of the hard decisions after a COMPLETE iteration, all scheduled rows (skipped rows are
+                // syndrome of the hard decisions after a COMPLETE iteration over the scheduled rows (skipped rows are
                 // satisfied by construction: their parity bit is the parity of the rest)
                 uint32_t bad = 0;
                 if (active && !cbDone) {
@@ -407,26 +582,20 @@ __global__ void __launch_bounds__(384, 1)
                         const int e0 = g.rowEdge0[row];
                         const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
                         uint32_t par = 0;
-                        for (int e = e0; e < e1; e++) {
-                            const uint32_t ew = g.edge[e];
-                            int p = m + (int)(ew & 0xffffu);
-                            p = (p >= Z) ? p - Z : p;
-                            par ^= FP<T>::sign(rcb[(int)(ew >> 16) * Z + p]);
-                        }
+                        for (int e = e0; e < e1; e++) par ^= FP<T>::sign(edge_posterior<T>(g, e, rb, mB, ZB));
                         if (row >= 4) {
-                            const T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
-                                                               : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
-                            par ^= FP<T>::sign(base[(size_t)PL_REXT * nT]);
+                            RowState<T> st;
+                            store.load(row, st);
+                            par ^= FP<T>::sign(st.rext);
                         }
                         bad |= par;
                     }
                 }
-                if (tid < a.cbPerCta) misc[tid] = 0;
+                if (tid < cbPerCta) misc[tid] = 0;
                 __syncthreads();
                 if (bad) misc[cbl] = 1;
                 __syncthreads();
                 if (lane_ok && misc[cbl] == 0) cbDone = true;
-                // CTA-wide exit when every hosted block is done
                 const int anyLeft = __syncthreads_or((active && !cbDone) ? 1 : 0);
                 if (!anyLeft) break;
             }
@@ -450,9 +619,9 @@ __global__ void __launch_bounds__(384, 1)
                 const int row = col - ksys;
                 T v;
                 if (row < a.numRows) {
-                    const T* base = (row < a.smemRows) ? (stateS + (size_t)row * NPLANES * nT + tid)
-                                                       : (stateG + (size_t)(row - a.smemRows) * NPLANES * nT + tid);
-                    v = base[(size_t)PL_REXT * nT];
+                    RowState<T> st;
+                    store.load(row, st);
+                    v = st.rext;
                 } else {
                     // skipped row: t_ext == 0 in every iteration, so its belief after the last iteration is
                     // 0.75 * parity * min(min_j |r_j|, 1e5) over the row's core edges evaluated on the final posteriors
@@ -461,10 +630,7 @@ __global__ void __launch_bounds__(384, 1)
                     T mn = (T)100000;
                     uint32_t par = 0;
                     for (int e = e0; e < e1; e++) {
-                        const uint32_t ew = g.edge[e];
-                        int p = m + (int)(ew & 0xffffu);
-                        p = (p >= Z) ? p - Z : p;
-                        const T rv = rcb[(int)(ew >> 16) * Z + p];
+                        const T rv = edge_posterior<T>(g, e, rb, mB, ZB);
                         mn = FP<T>::mn(mn, FP<T>::abs(rv));
                         par ^= FP<T>::sign(rv);
                     }
@@ -475,21 +641,12 @@ __global__ void __launch_bounds__(384, 1)
                 if (a.beliefs) reinterpret_cast<T*>(a.beliefs)[cb * (long long)a.outCols * Z + col * Z + m] = v;
             }
         }
-        if (a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA)) {
+        if (wantCrc) {
             // checkCrcAndMerge (ldpc.py:1610-1619) on the hard decisions still in shared memory
-            const int Lk = a.K - a.F;                       // code block without fillers
-            const int per = (a.C > 1) ? Lk - 24 : Lk;       // payload copied into the merged transport block
-            int P2 = 1;
-            while (P2 < Z) P2 <<= 1;
-            uint32_t* tree = misc + ((a.cbPerCta + 31) & ~31) + (size_t)cbl * P2;
-            const NrCrcPoly pb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
-            const uint32_t remCb = cb_crc<T>(rcb, Lk, Z, P2, m, active, tree, pb.poly, pb.len);
+            const uint32_t remCb = cb_crc<T>(rcb, Lk, Z, P2, m, active, tree, fac, polyCb.poly, polyCb.len);
             __syncthreads();
             uint32_t remA = remCb;
-            if (a.C > 1) {
-                const NrCrcPoly pa = nr_crc_poly(NRLDPC_CRC24A);
-                remA = cb_crc<T>(rcb, per, Z, P2, m, active, tree, pa.poly, pa.len);
-            }
+            if (a.C > 1) remA = cb_crc<T>(rcb, per, Z, P2, m, active, tree, fac + 16, polyA.poly, polyA.len);
             if (active) {
                 if (m == 0) {
                     if (a.cbCrcOk) a.cbCrcOk[cb] = (remCb == 0);
@@ -504,6 +661,11 @@ __global__ void __launch_bounds__(384, 1)
             }
         }
         __syncthreads();   // shared memory is reused by the next group
+    }
+    if (useTmem) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBaseSh), "r"((uint32_t)a.tmemCols) : "memory");
     }
 }
 
@@ -543,7 +705,21 @@ __global__ void nr_last_nonzero_kernel(const TIn* llr, long long numCb, long lon
     if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(lastCol, best);
 }
 
-template <typename T, typename TIn>
+// host: byte-offset edge table for compute type T
+template <typename T>
+void build_dec_graph(const NrGraph& g, NrDecGraph* d)
+{
+    memset(d, 0, sizeof(*d));
+    d->P = g.P; d->ncols = g.ncols; d->ksys = g.ksys; d->ncore = g.ncore; d->Z = g.Z;
+    for (int i = 0; i < NR_MAX_ROWS + 2; i++) d->rowEdge0[i] = g.rowEdge0[i];
+    for (int e = 0; e < g.rowEdge0[g.P]; e++) {
+        const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
+        d->tab[e].x = (col * g.Z + sh) * (uint32_t)sizeof(T);
+        d->tab[e].y = (col * g.Z + g.Z) * (uint32_t)sizeof(T);
+    }
+}
+
+template <typename T>
 int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s)
 {
     const int Z = g.Z;
@@ -551,26 +727,54 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     if ((long long)a.cbPerCta > a.numCb) a.cbPerCta = (int)a.numCb;
     int nT = a.cbPerCta * Z;
     nT = (nT + 31) & ~31;
-    const size_t rBytes = (size_t)a.cbPerCta * g.ncore * Z * sizeof(T);
-    const size_t rowBytes = (size_t)NPLANES * nT * sizeof(T);
+    const bool oneCb = (a.cbPerCta == 1 && nT == Z);
     int P2 = 1;
     while (P2 < Z) P2 <<= 1;
-    const size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + (size_t)a.cbPerCta * P2) * sizeof(uint32_t);
-    const size_t avail = (size_t)h->maxSmemOptin - 1024;
-    if (rBytes + miscBytes > avail) {
-        nr_set_error("decode: posteriors do not fit shared memory");
-        return NRLDPC_ERR_ARG;
+    const size_t rBytes = (size_t)a.cbPerCta * g.ncore * Z * sizeof(T);
+    const size_t rowBytes = (size_t)NPLANES * nT * sizeof(T);
+    const size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + 32 + (size_t)a.cbPerCta * P2) * sizeof(uint32_t);
+    // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
+    // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
+    int occ = h->decOcc > 0 ? h->decOcc : ((oneCb && sizeof(T) == 4) ? 2 : 1);
+    occ = max(1, min(occ, 2048 / nT));
+    if (sizeof(T) == 8) occ = 1;
+    // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs
+    a.tmemRows = 0;
+    a.tmemCols = 0;
+    if (oneCb && !h->noTmem) {
+        int cols = 32;
+        while (cols * 2 <= 512 / occ) cols *= 2;
+        const int RW = sizeof(T) == 4 ? 4 : 8;
+        const int wpq = ((nT >> 5) + 3) >> 2;
+        int rowsFit = cols / (wpq * RW);
+        if (rowsFit > a.numRows) rowsFit = a.numRows;
+        if (rowsFit > 0) {
+            int need = 32;
+            while (need < rowsFit * wpq * RW) need *= 2;
+            a.tmemRows = rowsFit;
+            a.tmemCols = need;
+        }
     }
-    int smemRows = (int)((avail - rBytes - miscBytes) / rowBytes);
-    if (smemRows > a.numRows) smemRows = a.numRows;
+    const int restRows = a.numRows - a.tmemRows;
+    size_t budget = (size_t)h->smemPerSM / occ - 1024;
+    budget = min(budget, (size_t)h->maxSmemOptin);
+    if (rBytes + miscBytes > budget) {
+        occ = 1;
+        budget = (size_t)h->maxSmemOptin;
+        if (rBytes + miscBytes > budget) {
+            nr_set_error("decode: posteriors do not fit shared memory");
+            return NRLDPC_ERR_ARG;
+        }
+    }
+    int smemRows = (int)((budget - rBytes - miscBytes) / rowBytes);
+    if (smemRows > restRows) smemRows = restRows;
     a.smemRows = smemRows;
     const size_t smem = rBytes + (size_t)smemRows * rowBytes + miscBytes;
     const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
-    // resident CTAs per SM are bounded by shared memory and by 2048 threads
-    int perSM = (int)(avail / (smem + 1024));
-    perSM = max(1, min(perSM, 2048 / nT));
+    int perSM = (int)((size_t)h->smemPerSM / (smem + 1024));
+    perSM = max(1, min(min(perSM, 2048 / nT), occ));
     long long grid = min(numGroups, (long long)h->numSMs * perSM);
-    const size_t needScratch = (size_t)grid * (size_t)(a.numRows - smemRows) * rowBytes;
+    const size_t needScratch = (size_t)grid * (size_t)(restRows - smemRows) * rowBytes;
     if (needScratch > h->scratchBytes) {
         if (h->scratch) NR_CUDA_CHECK(cudaFree(h->scratch));
         h->scratch = nullptr;
@@ -579,20 +783,28 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         h->scratchBytes = needScratch;
     }
     a.scratch = h->scratch;
-    auto kern = nr_decode_kernel<T, TIn>;
-    NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, nT, smem, s>>>(g, a);
+    NrDecGraph dg;
+    build_dec_graph<T>(g, &dg);
+    if (oneCb) {
+        auto kern = nr_decode_kernel<T, true>;
+        NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
+    } else {
+        auto kern = nr_decode_kernel<T, false>;
+        NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
+    }
     NR_CUDA_CHECK(cudaGetLastError());
     return NRLDPC_OK;
 }
 
 int dispatch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, int inDtype, int computeDtype, cudaStream_t s)
 {
-    if (computeDtype == NRLDPC_F32 && inDtype == NRLDPC_F32) return launch_decode<float, float>(h, g, a, s);
-    if (computeDtype == NRLDPC_F32 && inDtype == NRLDPC_F64) return launch_decode<float, double>(h, g, a, s);
-    if (computeDtype == NRLDPC_F64 && inDtype == NRLDPC_F64) return launch_decode<double, double>(h, g, a, s);
-    if (computeDtype == NRLDPC_F64 && inDtype == NRLDPC_F32) return launch_decode<double, float>(h, g, a, s);
-    nr_set_error("decode: bad dtype");
+    if (inDtype != NRLDPC_F32 && inDtype != NRLDPC_F64) { nr_set_error("decode: bad input dtype"); return NRLDPC_ERR_ARG; }
+    a.inF64 = (inDtype == NRLDPC_F64);
+    if (computeDtype == NRLDPC_F32) return launch_decode<float>(h, g, a, s);
+    if (computeDtype == NRLDPC_F64) return launch_decode<double>(h, g, a, s);
+    nr_set_error("decode: bad compute dtype");
     return NRLDPC_ERR_ARG;
 }
 
