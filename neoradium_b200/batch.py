@@ -82,6 +82,56 @@ class TbBatchCodec:
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
+    def decode_host(self, llr_host, numIter, out=None, chunks=4):
+        """Host-buffer entry point: llr_host is a float32|float64 [numTb, G'] HOST array (NumPy array or CPU torch
+        tensor; pinned memory gives full PCIe speed).  The batch is cut into `chunks` groups of transport blocks and
+        pipelined over three CUDA streams -- H2D copy of chunk i+1, fused decode of chunk i and D2H copy of the results of
+        chunk i-1 overlap -- and the call returns after everything has landed on the host.
+        `out` (optional) is a dict of preallocated host arrays/tensors {tb, cbOk, tbOk, iters} to write into (NumPy
+        `out=` convention; pinned buffers avoid a staging copy); otherwise fresh pinned tensors are allocated.
+        Returns the dict of host torch tensors (use .numpy() for zero-copy views)."""
+        x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(llr_host)
+        assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
+        numTb, Gp = x.shape
+        chunks = max(1, min(int(chunks), numTb))
+        bounds = [(numTb * i) // chunks for i in range(chunks + 1)]
+        key = (numTb, Gp, x.dtype, chunks)
+        st = getattr(self, '_pipe', None)
+        if st is None or st['key'] != key:
+            st = dict(key=key, h2d=torch.cuda.Stream(self.device), comp=torch.cuda.Stream(self.device),
+                      d2h=torch.cuda.Stream(self.device),
+                      din=[torch.empty((bounds[i + 1] - bounds[i], Gp), dtype=x.dtype, device=self.device)
+                           for i in range(chunks)],
+                      dout=[self.alloc_outputs(bounds[i + 1] - bounds[i]) for i in range(chunks)])
+            self._pipe = st
+        if out is None:
+            out = dict(tb=torch.empty((numTb, self.C * self.per), dtype=torch.int8).pin_memory(),
+                       cbOk=torch.empty((numTb, self.C), dtype=torch.uint8).pin_memory(),
+                       tbOk=torch.empty((numTb,), dtype=torch.uint8).pin_memory(),
+                       iters=torch.empty((numTb, self.C), dtype=torch.int32).pin_memory())
+        hout = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(v)) for k, v in out.items()}
+        cur = torch.cuda.current_stream(self.device)
+        for s_ in (st['h2d'], st['comp'], st['d2h']):
+            s_.wait_stream(cur)
+        for i in range(chunks):
+            lo, hi = bounds[i], bounds[i + 1]
+            with torch.cuda.stream(st['h2d']):
+                st['din'][i].copy_(x[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record()
+            with torch.cuda.stream(st['comp']):
+                st['comp'].wait_event(ev_in)
+                self.decode(st['din'][i], numIter, out=st['dout'][i])
+                ev_done = torch.cuda.Event()
+                ev_done.record()
+            with torch.cuda.stream(st['d2h']):
+                st['d2h'].wait_event(ev_done)
+                for k in ('tb', 'cbOk', 'tbOk', 'iters'):
+                    hout[k][lo:hi].copy_(st['dout'][i][k], non_blocking=True)
+        st['d2h'].synchronize()
+        return hout
+
+    # ------------------------------------------------------------------------------------------------------------------
     def accumulate(self, out, counters, refPayload=None):
         """counters int64[8] += {CBs, CB CRC fails, TBs, TB CRC fails, bit errors, sum iterations, 0, 0}."""
         numTb = out['tb'].shape[0]

@@ -380,7 +380,7 @@ class LdpcDecoder(LdpcBase):
         return tbBits, okHost
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decodeLLRs(self, llrs, txBlockSize, numIter=5, harq=None, precision=None, returnDevice=False):
+    def decodeLLRs(self, llrs, txBlockSize, numIter=5, harq=None, precision=None, returnDevice=False, out=None):
         """Fused RX chain (extension; the operation sequence of HarqCW.decodeLLRs, harq.py:165-173):
         recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') in one kernel pass.
 
@@ -388,12 +388,30 @@ class LdpcDecoder(LdpcBase):
         float64; NumPy array or a CUDA torch tensor).  Returns (txBlocks, cbCrc, tbCrc): decoded transport block(s)
         WITHOUT the 24 CRC bits ([A] or [numTb, A]), per-code-block CRC results ([C] / [numTb, C]) and the
         transport-block CRC24A result(s).  ``harq`` (single block only) supplies ``rv`` and the soft buffer exactly
-        as in ``recoverRate``."""
+        as in ``recoverRate``.  A [numTb, G] HOST batch takes the pipelined path (``TbBatchCodec.decode_host``: chunked
+        H2D / decode / D2H overlap); ``out`` may then carry preallocated (ideally pinned) host arrays
+        {tb [numTb, C*per], cbOk [numTb, C], tbOk [numTb], iters [numTb, C]} that receive the results."""
         self._rx_setup(txBlockSize)
         c, z = self.numCodeBlocks, self.liftingSize
         precision = precision or self.precision
         isT = isinstance(llrs, torch.Tensor)
         single = (llrs.dim() if isT else np.ndim(llrs)) == 1
+        onHost = (not isT) or llrs.device.type == 'cpu'
+        hdt = llrs.dtype if isT else np.asarray(llrs).dtype
+        if (not single) and onHost and harq is None and not returnDevice and \
+                hdt in (torch.float32, torch.float64, np.float32, np.float64):
+            from .batch import TbBatchCodec
+            x = llrs if isT else np.ascontiguousarray(llrs)
+            key = (txBlockSize, x.shape[1], precision, self.earlyStop)
+            codec = getattr(self, '_hostCodec', None)
+            if codec is None or self._hostCodecKey != key:
+                codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, x.shape[1], self.txLayers, self.nRef,
+                                     0, precision, self.earlyStop)
+                self._hostCodec, self._hostCodecKey = codec, key
+            res = codec.decode_host(x, numIter, out=out)
+            self.lastIterations = res['iters'].numpy().reshape(-1)
+            return (res['tb'].numpy()[:, :txBlockSize], res['cbOk'].numpy().view(np.bool_),
+                    res['tbOk'].numpy().view(np.bool_))
         x = _dev.to_dev(llrs)
         if x.dtype not in (torch.float32, torch.float64):
             x = x.to(torch.float64)
