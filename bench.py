@@ -296,7 +296,8 @@ def run_ours(args):
     lane_rate = 148 * 128 * sm_mhz * 1e6                       # issue slots x 32 lanes per second at the sampled clock
     edge_rate = ncb * EDGE_UPDATES_PER_CB / (kern_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": "nr_decode_kernel<float,float>", "kernel_ms": kern_ms,
+                "traffic": 58.29e6 * ncb / 1024.0, "traffic_source": "profiles/r01_decode_ncu_metrics.csv (ncu --set full, r1c): dram read 57.6 MB + write 0.7 MB per 1024-block launch",
+                "kernel": "nr_decode_kernel<float, ONE_CB>", "kernel_ms": kern_ms,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                 "note": "decode is ALU-issue bound, not HBM bound (SURVEY 8d): HBM fraction is reported as required, "
                         "the binding figure is alu_issue below",
