@@ -1,0 +1,39 @@
+"""BLER-vs-SNR Monte-Carlo sweep (BASELINE configs[4], reduced block count by default) sharded over the GPUs of one box:
+every rank generates, encodes, modulates, decodes and counts on its own device; one NCCL all-reduce of the int64[8]
+counter vector per SNR point.  torchrun --nproc-per-node N scripts/bler_sweep.py [--tbs 2048] [--early-stop]"""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'))
+import torch, torch.distributed as dist
+from neoradium_b200 import dist as nd
+from neoradium_b200.batch import TbBatchCodec
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--tbs", type=int, default=2048)
+ap.add_argument("--bg", type=int, default=1)
+ap.add_argument("--mod", default="16QAM")
+ap.add_argument("--A", type=int, default=8424 * 4 - 24)
+ap.add_argument("--rate", type=float, default=0.6)
+ap.add_argument("--iters", type=int, default=8)
+ap.add_argument("--snrs", default="7.0,7.4,7.8,8.0,8.2,8.4,8.6,8.8,9.0,9.4")
+ap.add_argument("--early-stop", action="store_true")
+args = ap.parse_args()
+rank, world, local = nd.env_rank_world()
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+qm = {'QPSK': 2, '16QAM': 4, '64QAM': 6, '256QAM': 8}[args.mod]
+g = int(-(-args.A / args.rate // qm) * qm)
+codec = TbBatchCodec(args.bg, args.mod, args.A, g, precision='fp32', earlyStop=args.early_stop)
+res = []
+for snr in [float(x) for x in args.snrs.split(",")]:
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    d = nd.bler_point(codec, args.tbs, snr, args.iters, seed=int(snr * 100), batch_tbs=256)
+    torch.cuda.synchronize(); d["snr_db"] = snr; d["seconds"] = time.perf_counter() - t0
+    res.append(d)
+    if rank == 0:
+        print("SNR %.1f dB  TBs %d  BLER %.4f  CB-BLER %.4f  BER %.2e  mean iters %.2f  %.2fs" % (
+            snr, d["txBlocks"], d["bler"], d["cbler"], d["bitErrors"] / (d["txBlocks"] * args.A), d["meanIterations"], d["seconds"]), flush=True)
+if rank == 0:
+    print(json.dumps({"config": vars(args), "world": world, "C": codec.C, "Zc": codec.Zc, "points": res}))
+if world > 1:
+    dist.destroy_process_group()
