@@ -35,11 +35,65 @@ namespace {
 
 // decoder view of the lifted graph: byte offsets instead of (column, shift), see process_row
 struct __align__(16) NrDecGraph {
-    int P, ncols, ksys, ncore, Z, pad[3];
+    int P, ncols, ksys, ncore, Z;
+    uint32_t S;                // ceil(2^32 / Z): lifted positions are tracked as 32-bit fixed-point fractions of Z
+    int pad[2];
     uint16_t rowEdge0[NR_MAX_ROWS + 2];
-    uint2 tab[NR_MAX_EDGES];   // x = (col*Z + shift)*sizeof(T), y = (col*Z + Z)*sizeof(T)
+    uint2 tab[NR_MAX_EDGES];   // x = (shift * S) mod 2^32, y = col*Z*sizeof(T)
 };
 
+// per-thread "argmin so far" record of a row pass: written with a predicated 64-bit (128-bit for fp64) shared-memory
+// store whenever a new strict minimum appears, read back once after the pass (LSU work instead of two ALU selects per edge)
+template <typename T>
+struct MinSlot;
+template <>
+struct __align__(8) MinSlot<float> {
+    float t;
+    uint32_t off;
+};
+template <>
+struct __align__(16) MinSlot<double> {
+    double t;
+    uint32_t off, pad;
+};
+// The record is written and read with inline PTX only, so that the compiler neither forwards it through registers
+// (which would bring the two selects per edge back as predicated moves) nor orders it against the posterior traffic.
+__device__ __forceinline__ void slot_init(uint32_t sa, float t, uint32_t off)
+{
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(sa), "r"(__float_as_uint(t)), "r"(off));
+}
+__device__ __forceinline__ void slot_update(uint32_t sa, float a, float min1, float t, uint32_t off)
+{
+    asm volatile("{.reg .pred p; setp.lt.f32 p, %0, %1; @p st.shared.v2.b32 [%2], {%3, %4};}" ::"f"(a), "f"(min1), "r"(sa),
+                 "r"(__float_as_uint(t)), "r"(off));
+}
+__device__ __forceinline__ MinSlot<float> slot_read(uint32_t sa, float)
+{
+    MinSlot<float> r;
+    uint32_t tb;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(tb), "=r"(r.off) : "r"(sa));
+    r.t = __uint_as_float(tb);
+    return r;
+}
+__device__ __forceinline__ void slot_init(uint32_t sa, double t, uint32_t off)
+{
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(sa), "l"(__double_as_longlong(t)), "l"((long long)off));
+}
+__device__ __forceinline__ void slot_update(uint32_t sa, double a, double min1, double t, uint32_t off)
+{
+    asm volatile("{.reg .pred p; setp.lt.f64 p, %0, %1; @p st.shared.v2.b64 [%2], {%3, %4};}" ::"d"(a), "d"(min1), "r"(sa),
+                 "l"(__double_as_longlong(t)), "l"((long long)off));
+}
+__device__ __forceinline__ MinSlot<double> slot_read(uint32_t sa, double)
+{
+    MinSlot<double> r;
+    long long tb, ob;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(tb), "=l"(ob) : "r"(sa));
+    r.t = __longlong_as_double(tb);
+    r.off = (uint32_t)ob;
+    r.pad = 0;
+    return r;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // exact arithmetic helpers
@@ -53,6 +107,9 @@ struct FP<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
     static __device__ __forceinline__ float mn(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float mx(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float from_u32(uint32_t v) { return __uint_as_float(v); }
+    static __device__ __forceinline__ uint32_t to_u32(float v) { return __float_as_uint(v); }
     static __device__ __forceinline__ uint32_t sign(float a) { return __float_as_uint(a) >> 31; }
     static __device__ __forceinline__ float flip(float mag, uint32_t bit)
     {
@@ -74,6 +131,9 @@ struct FP<double> {
     static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
     static __device__ __forceinline__ double abs(double a) { return fabs(a); }
     static __device__ __forceinline__ double mn(double a, double b) { return fmin(a, b); }
+    static __device__ __forceinline__ double mx(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double from_u32(uint32_t v) { return __hiloint2double(0, (int)v); }
+    static __device__ __forceinline__ uint32_t to_u32(double v) { return (uint32_t)__double2loint(v); }
     static __device__ __forceinline__ uint32_t sign(double a) { return ((uint32_t)__double2hiint(a)) >> 31; }
     static __device__ __forceinline__ double flip(double mag, uint32_t bit)
     {
@@ -198,116 +258,138 @@ __device__ __forceinline__ void tmem_st(const RowState<double>& st, uint32_t tad
 
 // ---------------------------------------------------------------------------------------------------------------
 // one layer for one lifted check.  D = row degree, EXT = last edge is the thread-private extension column.
-// sw layout: bit (D-1-j) = sign of the stored message of edge j, bits 24..28 = argmin edge.
 //
-// Instruction budget per edge (the kernel is bound by the half-rate ALU pipe):
-//   address  : u = mB + tab.x; if (u >= tab.y) u -= ZB        (tab = byte offsets precomputed on the host)
+// State of a check between iterations: alpha*min1, alpha*min2, the sign bits of its D messages (bit D-1-j = edge j)
+// and the shared-memory byte offset of the edge that received min2 (the argmin).  EXT rows keep the offset in bits
+// 12.. of the sign word, core rows (D = 19, no private column) in the otherwise unused `rext` word.
+//
+// Pipe budget per edge (measured on B200, scripts/pipe_ubench.cu: the ALU pipe issues LOP3/SHF/SEL/ISETP/FSETP every
+// 2nd clock per SM sub-partition, 2-input FMNMX every clock; FADD/FMUL run every clock and IMAD every 2nd on the FMA
+// pipe; the kernel was ALU-pipe bound, so work is moved off that pipe wherever arithmetic allows):
+//   address  : w = m*S + shift*S (IMAD) is the lifted position (m + shift) mod Z as a 32-bit fixed-point fraction --
+//              the wrap-around is the integer overflow; byte offset = hi32(w * Z*sizeof(T)) + column base (IMAD.HI).
+//              No compare/select, nothing on the ALU pipe.
 //   gather   : LDS
-//   old msg  : (j == oldIdx ? m2 : m1) ^ (sign bit moved to bit 31), FADD
+//   old msg  : (offset == old argmin offset ? m2 : m1) ^ (sign bit moved to bit 31), FADD
 //   signs    : one funnel shift collects the sign bit of t
-//   two-min  : compare, 2 selects, 1 min, 1 index select
-//   new msg  : (j == idx ? m2' : m1') ^ (t & 0x80000000) with the parity pre-applied to m1', m2';  FADD;  STS
+//   two-min  : min1/min2 VALUES by three FMNMX; the argmin (signed t and offset) is not tracked in registers: a
+//              predicated STS.64 drops it into the thread's MinSlot whenever |t| < min1 (strict: first minimum)
+//   new msg  : every edge gets m1' ^ sign(t) (LOP3, FADD, STS); afterwards the argmin edge alone is re-written with
+//              m2' from the MinSlot record -- no per-edge index compare/select.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int D, bool EXT>
-__device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t mB,
-                                            uint32_t ZB, RowState<T>& st)
+__device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32_t ZB, uint2 tb)
 {
+    uint32_t w, off;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(w) : "r"(m), "r"(S), "r"(tb.x));
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"(w), "r"(ZB), "r"(tb.y));
+    return off;
+}
+
+template <typename T, int D, bool EXT>
+__device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t m,
+                                            uint32_t ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff)
+{
+    constexpr int OFF_SHIFT = 12;   // EXT rows: D <= 10 sign bits, then the argmin offset
     T t[D];
     uint32_t off[D];
     T m1s = st.m1s, m2s = st.m2s;
     const uint32_t sw = st.sw;
-    const int oldIdx = (int)(sw >> 24);
+    const uint32_t oldOff = EXT ? (sw >> OFF_SHIFT) : FP<T>::to_u32(st.rext);
+    const uint32_t S = g.S;
     T min1 = (T)0, min2 = FP<T>::inf();
-    int idx = 0;
     uint32_t nsw = 0;
 #pragma unroll
     for (int j = 0; j < D; j++) {
         T rv;
         if (EXT && j == D - 1) {
             rv = st.rext;
-            off[j] = 0;
+            off[j] = dummyOff;
         } else {
-            const uint2 tb = g.tab[e0 + j];
-            uint32_t u = mB + tb.x;
-            u = (u >= tb.y) ? u - ZB : u;
-            off[j] = u;
-            rv = *reinterpret_cast<const T*>(rb + u);
+            off[j] = lifted_offset(m, S, ZB, g.tab[e0 + j]);
+            rv = *reinterpret_cast<const T*>(rb + off[j]);
         }
         {   // in the first iteration the state is all zero: r - (+0) == r exactly
-            const T mag = (j == oldIdx) ? m2s : m1s;
+            const T mag = (off[j] == oldOff) ? m2s : m1s;
             t[j] = FP<T>::sub(rv, FP<T>::flipbits(mag, sw << (31 - (D - 1 - j))));
         }
         const T a = FP<T>::abs(t[j]);
         nsw = __funnelshift_l(FP<T>::hibits(t[j]), nsw, 1);   // (nsw << 1) | sign(t_j)
         if (j == 0) {
             min1 = a;
+            slot_init(slot, t[j], off[j]);
         } else {
-            const bool lt = a < min1;   // strict: keeps the FIRST minimum (np.argmin)
-            min2 = lt ? min1 : FP<T>::mn(min2, a);
-            min1 = lt ? a : min1;
-            idx = lt ? j : idx;
+            slot_update(slot, a, min1, t[j], off[j]);   // strict a < min1: keeps the FIRST minimum (np.argmin)
+            min2 = FP<T>::mn(min2, FP<T>::mx(min1, a));
+            min1 = FP<T>::mn(min1, a);
         }
     }
+    const MinSlot<T> best = slot_read(slot, (T)0);
     // the reference bumps the signed minimum by 1e5 and takes |.| before searching the second minimum (ldpc.py:1563)
-    {
-        const T tq = FP<T>::flip(min1, (nsw >> (D - 1 - idx)) & 1u);
-        min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(tq, (T)100000)));
-    }
+    min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(best.t, (T)100000)));
     const uint32_t par = __popc(nsw) & 1u;
     const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;   // sign of new message j = sign_j * parity
     m1s = FP<T>::mul(min1, (T)0.75);
     m2s = FP<T>::mul(min2, (T)0.75);
-    T m1p = FP<T>::flip(m1s, par), m2p = FP<T>::flip(m2s, par);
-    FP<T>::opaque(m1p);   // keep the parity folded into the two candidates instead of one extra XOR per edge
-    FP<T>::opaque(m2p);
+    // parity folded into the two candidates by an exact multiplication with +-1 (an XOR here would be re-associated
+    // by ptxas into one extra LOP3 per edge)
+    const T psign = FP<T>::flip((T)1, par);
+    const T m1p = FP<T>::mul(m1s, psign), m2p = FP<T>::mul(m2s, psign);
+    T rext = (T)0;
 #pragma unroll
     for (int j = 0; j < D; j++) {
-        const T mag = (j == idx) ? m2p : m1p;
-        const T nv = FP<T>::add(t[j], FP<T>::flipbits(mag, FP<T>::hibits(t[j])));
+        const T nv = FP<T>::add(t[j], FP<T>::flipbits(m1p, FP<T>::hibits(t[j])));
         if (EXT && j == D - 1)
-            st.rext = nv;
+            rext = nv;
         else
             *reinterpret_cast<T*>(rb + off[j]) = nv;
     }
+    {   // the argmin edge takes the second minimum (program order after the generic store to the same word)
+        const T nv = FP<T>::add(best.t, FP<T>::flipbits(m2p, FP<T>::hibits(best.t)));
+        *reinterpret_cast<T*>(rb + best.off) = nv;   // lands in the thread's dummy word when the argmin is private
+        if (EXT) rext = (best.off == dummyOff) ? nv : rext;
+    }
     st.m1s = m1s;
     st.m2s = m2s;
-    st.sw = msw | ((uint32_t)idx << 24);
+    if (EXT) {
+        st.sw = msw | (best.off << OFF_SHIFT);
+        st.rext = rext;
+    } else {
+        st.sw = msw;
+        st.rext = FP<T>::from_u32(best.off);
+    }
 }
 
 template <typename T>
-__device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t mB, uint32_t ZB,
-                                             RowState<T>& st)
+__device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t m, uint32_t ZB,
+                                             RowState<T>& st, uint32_t slot, uint32_t dummyOff)
 {
     const int e0 = g.rowEdge0[row];
     const int deg = g.rowEdge0[row + 1] - e0;
     if (row >= 4) {
         switch (deg) {
-            case 3: process_row<T, 3, true>(g, e0, rb, mB, ZB, st); break;
-            case 4: process_row<T, 4, true>(g, e0, rb, mB, ZB, st); break;
-            case 5: process_row<T, 5, true>(g, e0, rb, mB, ZB, st); break;
-            case 6: process_row<T, 6, true>(g, e0, rb, mB, ZB, st); break;
-            case 7: process_row<T, 7, true>(g, e0, rb, mB, ZB, st); break;
-            case 8: process_row<T, 8, true>(g, e0, rb, mB, ZB, st); break;
-            case 9: process_row<T, 9, true>(g, e0, rb, mB, ZB, st); break;
-            default: process_row<T, 10, true>(g, e0, rb, mB, ZB, st); break;
+            case 3: process_row<T, 3, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 4: process_row<T, 4, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 5: process_row<T, 5, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 6: process_row<T, 6, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 7: process_row<T, 7, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 8: process_row<T, 8, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 9: process_row<T, 9, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            default: process_row<T, 10, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
         }
     } else {
         switch (deg) {
-            case 8: process_row<T, 8, false>(g, e0, rb, mB, ZB, st); break;
-            case 10: process_row<T, 10, false>(g, e0, rb, mB, ZB, st); break;
-            default: process_row<T, 19, false>(g, e0, rb, mB, ZB, st); break;
+            case 8: process_row<T, 8, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 10: process_row<T, 10, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            default: process_row<T, 19, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
         }
     }
 }
 
-// posterior addressed by edge `e` for lifted index byte offset mB
+// posterior addressed by edge `e` for lifted index m
 template <typename T>
-__device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t mB, uint32_t ZB)
+__device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t m, uint32_t ZB)
 {
-    const uint2 tb = g.tab[e];
-    uint32_t u = mB + tb.x;
-    u = (u >= tb.y) ? u - ZB : u;
-    return *reinterpret_cast<const T*>(rb + u);
+    return *reinterpret_cast<const T*>(rb + lifted_offset(m, g.S, ZB, g.tab[e]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -442,6 +524,11 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     int P2 = 1;
     while (P2 < Z) P2 <<= 1;
     uint32_t* tree = misc + flagsLen + 32 + (size_t)cbl * P2;
+    // per-thread argmin record + dummy word (16-byte aligned region after the CRC trees)
+    const size_t slotOfs = ((size_t)(reinterpret_cast<unsigned char*>(misc + flagsLen + 32 + (size_t)cbPerCta * P2) - smemRaw) + 15) & ~(size_t)15;
+    MinSlot<T>* slotP = reinterpret_cast<MinSlot<T>*>(smemRaw + slotOfs) + tid;
+    const uint32_t slot = (uint32_t)__cvta_generic_to_shared(slotP);
+    T* dummyW = reinterpret_cast<T*>(slotP - tid + nT) + tid;
     const int globRows = a.numRows - a.tmemRows - a.smemRows;
     T* stateG = reinterpret_cast<T*>(a.scratch) + (size_t)blockIdx.x * (size_t)globRows * NPLANES * nT;
     T* rcb = rs + (size_t)cbl * ncore * Z;
@@ -472,8 +559,9 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         store.nT = nT;
     }
     char* rb = reinterpret_cast<char*>(rcb);
-    const uint32_t mB = (uint32_t)m * (uint32_t)sizeof(T);
+    const uint32_t mU = (uint32_t)m;
     const uint32_t ZB = (uint32_t)Z * (uint32_t)sizeof(T);
+    const uint32_t dummyOff = (uint32_t)(reinterpret_cast<char*>(dummyW) - rb);
     const int ksys = g.ksys;
 
     const bool wantCrc = a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA);
@@ -567,7 +655,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 if (ONE_CB || (active && !cbDone)) {
                     RowState<T> st;
                     store.load(row, st);
-                    dispatch_row<T>(g, row, rb, mB, ZB, st);
+                    dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff);
                     store.store(row, st);
                 }
                 __syncthreads();
@@ -582,7 +670,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                         const int e0 = g.rowEdge0[row];
                         const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
                         uint32_t par = 0;
-                        for (int e = e0; e < e1; e++) par ^= FP<T>::sign(edge_posterior<T>(g, e, rb, mB, ZB));
+                        for (int e = e0; e < e1; e++) par ^= FP<T>::sign(edge_posterior<T>(g, e, rb, mU, ZB));
                         if (row >= 4) {
                             RowState<T> st;
                             store.load(row, st);
@@ -630,7 +718,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                     T mn = (T)100000;
                     uint32_t par = 0;
                     for (int e = e0; e < e1; e++) {
-                        const T rv = edge_posterior<T>(g, e, rb, mB, ZB);
+                        const T rv = edge_posterior<T>(g, e, rb, mU, ZB);
                         mn = FP<T>::mn(mn, FP<T>::abs(rv));
                         par ^= FP<T>::sign(rv);
                     }
@@ -712,10 +800,11 @@ void build_dec_graph(const NrGraph& g, NrDecGraph* d)
     memset(d, 0, sizeof(*d));
     d->P = g.P; d->ncols = g.ncols; d->ksys = g.ksys; d->ncore = g.ncore; d->Z = g.Z;
     for (int i = 0; i < NR_MAX_ROWS + 2; i++) d->rowEdge0[i] = g.rowEdge0[i];
+    d->S = (uint32_t)((0x100000000ULL + (uint64_t)g.Z - 1) / (uint64_t)g.Z);   // ceil(2^32 / Z); Z >= 2
     for (int e = 0; e < g.rowEdge0[g.P]; e++) {
         const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
-        d->tab[e].x = (col * g.Z + sh) * (uint32_t)sizeof(T);
-        d->tab[e].y = (col * g.Z + g.Z) * (uint32_t)sizeof(T);
+        d->tab[e].x = (uint32_t)((uint64_t)sh * d->S);   // mod 2^32
+        d->tab[e].y = col * g.Z * (uint32_t)sizeof(T);
     }
 }
 
@@ -732,7 +821,8 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     while (P2 < Z) P2 <<= 1;
     const size_t rBytes = (size_t)a.cbPerCta * g.ncore * Z * sizeof(T);
     const size_t rowBytes = (size_t)NPLANES * nT * sizeof(T);
-    const size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + 32 + (size_t)a.cbPerCta * P2) * sizeof(uint32_t);
+    const size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + 32 + (size_t)a.cbPerCta * P2) * sizeof(uint32_t) + 16 +
+                             (size_t)nT * (sizeof(MinSlot<T>) + sizeof(T));
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
     int occ = h->decOcc > 0 ? h->decOcc : ((oneCb && sizeof(T) == 4) ? 2 : 1);
