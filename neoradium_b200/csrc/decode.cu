@@ -25,6 +25,7 @@
 // makes the raw sign bit equal to (t < 0) for every t the recursion can produce.
 #include <string.h>
 
+#include "nr_bg_tables.h"
 #include "nrldpc_internal.cuh"
 
 #ifndef NR_DEC_MIN_CTAS
@@ -385,6 +386,41 @@ __device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Static schedule (fp32, one block per CTA): the rows of the base graph are unrolled at compile time, so the edge
+// table entries are constant-bank operands of the address IMADs (no LDC, no degree dispatch) and the Tensor-Memory
+// address of a row's state is an immediate.  The code of one iteration is ~90 KB for BG1; all warps of an SM walk it
+// in step (one barrier per row), so it streams through the instruction cache once per iteration.
+// ---------------------------------------------------------------------------------------------------------------
+template <int BG>
+struct BgRows {
+    static constexpr int P = BG == 1 ? NR_BG1_ROWS : NR_BG2_ROWS;
+    static __host__ __device__ constexpr int deg(int r) { return BG == 1 ? NR_BG1_ROW_DEG[r] : NR_BG2_ROW_DEG[r]; }
+    static __host__ __device__ constexpr int e0(int r)
+    {
+        int e = 0;
+        for (int i = 0; i < r; i++) e += deg(i);
+        return e;
+    }
+};
+
+template <typename T, int BG, int ROW, typename Store>
+__device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, uint32_t ZB,
+                                                const Store& store, uint32_t slot, uint32_t dummyOff)
+{
+    if constexpr (ROW < BgRows<BG>::P) {
+        if (ROW >= 4 && ROW >= numRows) return;   // numRows >= 4 always
+        constexpr int D = BgRows<BG>::deg(ROW);
+        constexpr int E0 = BgRows<BG>::e0(ROW);
+        RowState<T> st;
+        store.load(ROW, st);
+        process_row<T, D, (ROW >= 4)>(g, E0, rb, m, ZB, st, slot, dummyOff);
+        store.store(ROW, st);
+        __syncthreads();
+        run_rows_static<T, BG, ROW + 1>(g, numRows, rb, m, ZB, store, slot, dummyOff);
+    }
+}
+
 // posterior addressed by edge `e` for lifted index m
 template <typename T>
 __device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t m, uint32_t ZB)
@@ -501,7 +537,7 @@ __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
 // the kernel.  ONE_CB: exactly one code block per CTA and blockDim.x == Z (Z a multiple of 32): no thread is ever
 // idle, so the row bodies run in convergent code and the (column, shift) table is read through the uniform datapath.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool ONE_CB>
+template <typename T, bool ONE_CB, int SBG>
 __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
@@ -651,14 +687,18 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         int itersDone = 0;
         bool cbDone = false;
         for (int it = 0; it < a.numIter; it++) {
-            for (int row = 0; row < a.numRows; row++) {
-                if (ONE_CB || (active && !cbDone)) {
-                    RowState<T> st;
-                    store.load(row, st);
-                    dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff);
-                    store.store(row, st);
+            if constexpr (SBG != 0) {
+                run_rows_static<T, SBG, 0>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff);
+            } else {
+                for (int row = 0; row < a.numRows; row++) {
+                    if (ONE_CB || (active && !cbDone)) {
+                        RowState<T> st;
+                        store.load(row, st);
+                        dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff);
+                        store.store(row, st);
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
             if (!cbDone) itersDone = it + 1;
             if (a.flags & NRLDPC_DEC_EARLY_STOP) {
@@ -875,12 +915,21 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     a.scratch = h->scratch;
     NrDecGraph dg;
     build_dec_graph<T>(g, &dg);
-    if (oneCb) {
-        auto kern = nr_decode_kernel<T, true>;
+    const bool staticRows = oneCb && sizeof(T) == 4 && !h->noStaticRows;
+    if (staticRows && g.P == NR_BG1_ROWS) {
+        auto kern = nr_decode_kernel<T, true, (sizeof(T) == 4 ? 1 : 0)>;
+        NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
+    } else if (staticRows) {
+        auto kern = nr_decode_kernel<T, true, (sizeof(T) == 4 ? 2 : 0)>;
+        NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
+    } else if (oneCb) {
+        auto kern = nr_decode_kernel<T, true, 0>;
         NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
     } else {
-        auto kern = nr_decode_kernel<T, false>;
+        auto kern = nr_decode_kernel<T, false, 0>;
         NR_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)grid, nT, smem, s>>>(dg, a);
     }
