@@ -38,7 +38,8 @@ namespace {
 struct __align__(16) NrDecGraph {
     int P, ncols, ksys, ncore, Z;
     uint32_t S;                // ceil(2^32 / Z): lifted positions are tracked as 32-bit fixed-point fractions of Z
-    int pad[2];
+    uint32_t one;              // 1, opaque to the compiler: keeps the column-base add an IMAD (FMA pipe) instead of an ALU add
+    int pad[1];
     uint16_t rowEdge0[NR_MAX_ROWS + 2];
     uint2 tab[NR_MAX_EDGES];   // x = (shift * S) mod 2^32, y = col*Z*sizeof(T)
 };
@@ -278,11 +279,13 @@ __device__ __forceinline__ void tmem_st(const RowState<double>& st, uint32_t tad
 //   new msg  : every edge gets m1' ^ sign(t) (LOP3, FADD, STS); afterwards the argmin edge alone is re-written with
 //              m2' from the MinSlot record -- no per-edge index compare/select.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32_t ZB, uint2 tb)
+__device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32_t ZB, uint32_t one, uint2 tb)
 {
-    uint32_t w, off;
+    // (a multiply-high WITH addend needs a zeroed even/odd register pair in SASS: two extra moves per edge)
+    uint32_t w, p, off;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(w) : "r"(m), "r"(S), "r"(tb.x));
-    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(off) : "r"(w), "r"(ZB), "r"(tb.y));
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(p) : "r"(w), "r"(ZB));
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(off) : "r"(p), "r"(one), "r"(tb.y));
     return off;
 }
 
@@ -296,7 +299,7 @@ __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* _
     T m1s = st.m1s, m2s = st.m2s;
     const uint32_t sw = st.sw;
     const uint32_t oldOff = EXT ? (sw >> OFF_SHIFT) : FP<T>::to_u32(st.rext);
-    const uint32_t S = g.S;
+    const uint32_t S = g.S, one = g.one;
     T min1 = (T)0, min2 = FP<T>::inf();
     uint32_t nsw = 0;
 #pragma unroll
@@ -306,7 +309,7 @@ __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* _
             rv = st.rext;
             off[j] = dummyOff;
         } else {
-            off[j] = lifted_offset(m, S, ZB, g.tab[e0 + j]);
+            off[j] = lifted_offset(m, S, ZB, one, g.tab[e0 + j]);
             rv = *reinterpret_cast<const T*>(rb + off[j]);
         }
         {   // in the first iteration the state is all zero: r - (+0) == r exactly
@@ -425,7 +428,7 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
 template <typename T>
 __device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t m, uint32_t ZB)
 {
-    return *reinterpret_cast<const T*>(rb + lifted_offset(m, g.S, ZB, g.tab[e]));
+    return *reinterpret_cast<const T*>(rb + lifted_offset(m, g.S, ZB, g.one, g.tab[e]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -638,40 +641,119 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 if (a.softBuf) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
             }
             const int colEnd = (a.rm && sb) ? g.ncols : lastCol;   // a soft buffer is combined over its whole length
-            for (int col = 2; col < colEnd; col++) {
-                const int n = (col - 2) * Z + m;   // index in the punctured coded block
-                T v = (T)0;
-                if (!a.rm) {
-                    if (col - 2 < a.inCols) v = load_llr<T>(a.llr, cb * a.llrStride + n, a.inF64);
-                } else if (n < a.ncb) {
-                    if (n >= sysLen && n < sysLen + a.F) {
-                        v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
-                    } else {
-                        const int q = (n < sysLen) ? n : n - a.F;   // index in the filler-less circular buffer
-                        T acc = sb ? sb[q] : (T)0;
-                        int i = q - a.k0;
-                        if (i < 0) i += L;
-                        for (; i < E; i += L) {       // one term per wrap, ascending => the reference's += order
-                            const int b = i / Eq, sI = i - b * Eq;   // de-interleave: stream index s*qm + b
-                            const long long xi = (long long)sI * a.qm + b;
-                            const T xv = (xi < xAvail) ? load_llr<T>(a.llr, xBase + xi, a.inF64) : (T)0;
-                            acc = FP<T>::add(acc, xv);
+            // de-interleaver division i / Eq: float reciprocal + one correction step (exact for i < 2^24)
+            const bool smallE = E < (1 << 24);
+            const float rcpEq = 1.0f / (float)Eq;
+            const int xAvailI = (int)(xAvail < 0 ? 0 : (xAvail > (long long)E ? (long long)E : xAvail));
+            auto load_cols = [&](auto tin) {
+                using TIn = decltype(tin);
+                const TIn* __restrict__ x = reinterpret_cast<const TIn*>(a.llr) + (a.rm ? xBase : cb * a.llrStride);
+                int n = m;   // index in the punctured coded block
+                for (int col = 2; col < colEnd; col++, n += Z) {
+                    T v = (T)0;
+                    if (!a.rm) {
+                        if (col - 2 < a.inCols) v = (T)x[n];
+                    } else if (n < a.ncb) {
+                        if (n >= sysLen && n < sysLen + a.F) {
+                            v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
+                        } else {
+                            const int q = (n < sysLen) ? n : n - a.F;   // index in the filler-less circular buffer
+                            T acc = sb ? sb[q] : (T)0;
+                            int i = q - a.k0;
+                            if (i < 0) i += L;
+                            for (; i < E; i += L) {       // one term per wrap, ascending => the reference's += order
+                                int b;                    // de-interleave: stream index s*qm + b, i = b*Eq + s
+                                if (smallE) {
+                                    b = (int)((float)i * rcpEq);
+                                    const int r = i - b * Eq;
+                                    b += (r >= Eq) ? 1 : 0;
+                                    b -= (r < 0) ? 1 : 0;
+                                } else {
+                                    b = i / Eq;
+                                }
+                                const int xi = (i - b * Eq) * a.qm + b;
+                                const T xv = (xi < xAvailI) ? (T)x[xi] : (T)0;
+                                acc = FP<T>::add(acc, xv);
+                            }
+                            if (sb) sb[q] = acc;
+                            v = acc;
                         }
-                        if (sb) sb[q] = acc;
-                        v = acc;
+                    }
+                    if (col >= lastCol) continue;           // beyond the scheduled rows: only the soft buffer is updated
+                    v = (v > (T)1e10) ? (T)1e10 : v;        // np.clip(., -1e10, 1e10), ldpc.py:1536
+                    v = (v < (T)-1e10) ? (T)-1e10 : v;
+                    v = FP<T>::add(v, (T)0);                 // -0.0 -> +0.0 (see header)
+                    if (col < ncore) {
+                        rcb[col * Z + m] = v;
+                    } else {
+                        RowState<T> st0;   // messages start at +0 (ldpc.py:1543), posterior of the extension column = its LLR
+                        st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = v;
+                        store.store(col - ksys, st0);
                     }
                 }
-                if (col >= lastCol) continue;           // beyond the scheduled rows: only the soft buffer is updated
-                v = (v > (T)1e10) ? (T)1e10 : v;        // np.clip(., -1e10, 1e10), ldpc.py:1536
-                v = (v < (T)-1e10) ? (T)-1e10 : v;
-                v = FP<T>::add(v, (T)0);                 // -0.0 -> +0.0 (see header)
-                if (col < ncore) {
-                    rcb[col * Z + m] = v;
-                } else {
-                    RowState<T> st0;   // messages start at +0 (ldpc.py:1543), posterior of the extension column = its LLR
-                    st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = v;
-                    store.store(col - ksys, st0);
+            };
+            if (a.rm && !sb && !a.inF64 && smallE) {
+                // common case (fp32 stream, no HARQ history): same arithmetic, none of the generic bookkeeping
+                const float* __restrict__ x = reinterpret_cast<const float*>(a.llr) + xBase;
+                const int ncb = a.ncb, F = a.F, k0 = a.k0, qm = a.qm;
+                // stream index of circular-buffer position i (de-interleaver), i < E
+                auto stream_index = [&](int i) {
+                    int b = (int)((float)i * rcpEq);
+                    const int r = i - b * Eq;
+                    b += (r >= Eq) ? 1 : 0;
+                    b -= (r < 0) ? 1 : 0;
+                    return (i - b * Eq) * qm + b;
+                };
+                constexpr int CH = 8;   // columns in flight: the HBM latency of the gather is paid once per chunk
+                for (int col0 = 2; col0 < lastCol; col0 += CH) {
+                    T v[CH];
+                    int inext[CH];
+#pragma unroll
+                    for (int c = 0; c < CH; c++) {
+                        const int n = (col0 + c - 2) * Z + m;
+                        v[c] = (T)0;
+                        inext[c] = E;   // nothing more to add
+                        if (col0 + c < lastCol && n < ncb) {
+                            const int nf = n - sysLen;   // >= 0: at or behind the filler gap
+                            if ((unsigned)nf < (unsigned)F) {
+                                v[c] = (T)1e10;          // LARGE_LLR after the clip
+                            } else {
+                                int i = n - (nf >= 0 ? F : 0) - k0;
+                                i += (i < 0) ? L : 0;
+                                if (i < E) {
+                                    const int xi = stream_index(i);
+                                    v[c] = (xi < xAvailI) ? (T)x[xi] : (T)0;   // 0 + x == x exactly
+                                    inext[c] = i + L;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < CH; c++) {
+                        if (col0 + c < lastCol) {
+                            T acc = v[c];
+                            for (int i = inext[c]; i < E; i += L) {   // further wraps (E > Ncb - F), ascending order
+                                const int xi = stream_index(i);
+                                acc = FP<T>::add(acc, (xi < xAvailI) ? (T)x[xi] : (T)0);
+                            }
+                            acc = FP<T>::mn(acc, (T)1e10);
+                            acc = FP<T>::mx(acc, (T)-1e10);
+                            acc = FP<T>::add(acc, (T)0);   // -0.0 -> +0.0 (see header)
+                            const int col = col0 + c;
+                            if (col < ncore) {
+                                rcb[col * Z + m] = acc;
+                            } else {
+                                RowState<T> st0;
+                                st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = acc;
+                                store.store(col - ksys, st0);
+                            }
+                        }
+                    }
                 }
+            } else if (a.inF64) {
+                load_cols(double());
+            } else {
+                load_cols(float());
             }
             for (int row = 0; row < 4; row++) {
                 RowState<T> st0;
@@ -840,6 +922,7 @@ void build_dec_graph(const NrGraph& g, NrDecGraph* d)
     memset(d, 0, sizeof(*d));
     d->P = g.P; d->ncols = g.ncols; d->ksys = g.ksys; d->ncore = g.ncore; d->Z = g.Z;
     for (int i = 0; i < NR_MAX_ROWS + 2; i++) d->rowEdge0[i] = g.rowEdge0[i];
+    d->one = 1;
     d->S = (uint32_t)((0x100000000ULL + (uint64_t)g.Z - 1) / (uint64_t)g.Z);   // ceil(2^32 / Z); Z >= 2
     for (int e = 0; e < g.rowEdge0[g.P]; e++) {
         const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
