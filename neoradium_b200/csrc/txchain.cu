@@ -2,6 +2,8 @@
 // Replaces LdpcEncoder.encode (neoradium/ldpc.py:1057-1090), LdpcEncoder.rateMatch (ldpc.py:1128-1159) and a correct
 // LdpcBase.isValidCodedBlock (ldpc.py:825-843).  All three are HBM-bound byte kernels: coalesced int8 loads/stores
 // along the lifted index, the code block staged in shared memory, circulant shifts as index arithmetic.
+#include <stdlib.h>
+
 #include "nrldpc_internal.cuh"
 
 namespace {
@@ -81,6 +83,142 @@ __global__ void __launch_bounds__(TX_THREADS)
                 const uint32_t p = row_xor(g, g.rowEdge0[r], g.rowEdge0[r + 1], s, m, Z, ncore);
                 o[(long long)(k + r - firstCol) * Z + m] = (signed char)p;
             }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bit-packed encoder (Z a multiple of 16: every lifting size >= 128 and 16/32/48/64/80/96/112).
+//
+// One code block per 128-thread CTA (5-6 KB of shared memory, so an SM keeps 16 of them in flight).  The K input
+// bytes are read as 16-byte vectors and squeezed to 16 bits each with an integer multiply; every column of degree > 1
+// is kept DOUBLED in shared memory (bits 0..Z-1 followed by the same Z bits), so the circulant rotation rot(x, s) is
+// "read Z bits at bit offset s" -- two consecutive words and one funnel shift per 32 result bits, no wrap-around
+// logic, for every Z.  A row is the XOR of such words; the result bits are spread back to one byte per bit with one
+// multiply per 4 bytes and leave as 16-byte vector stores.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int ENC_THREADS = 128;
+
+__device__ __forceinline__ uint32_t pack4(uint32_t w)   // 4 bytes (0/1) -> 4 bits, byte 0 at bit 0
+{
+    return ((w & 0x01010101u) * 0x01020408u) >> 24;
+}
+__device__ __forceinline__ uint32_t pack16(uint4 v)
+{
+    return pack4(v.x) | (pack4(v.y) << 4) | (pack4(v.z) << 8) | (pack4(v.w) << 12);
+}
+__device__ __forceinline__ uint32_t spread4(uint32_t nib)   // 4 bits -> 4 bytes (0/1)
+{
+    return ((nib & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+// 32 bits of rot(x, s) starting at result bit 32*i, from the doubled column d
+__device__ __forceinline__ uint32_t rot_word(const uint32_t* d, int s, int i)
+{
+    const int o = s + 32 * i;
+    return __funnelshift_r(d[o >> 5], d[(o >> 5) + 1], o & 31);
+}
+// write result word `v` (bits 32*i .. of a Z-bit column) into the doubled column d (16-bit granularity: Z % 16 == 0)
+__device__ __forceinline__ void store_doubled(uint32_t* d, int i, uint32_t v, int Zh)
+{
+    unsigned short* dh = reinterpret_cast<unsigned short*>(d);
+    const int h0 = 2 * i;
+    if (h0 < Zh) { dh[h0] = (unsigned short)v; dh[h0 + Zh] = (unsigned short)v; }
+    if (h0 + 1 < Zh) { dh[h0 + 1] = (unsigned short)(v >> 16); dh[h0 + 1 + Zh] = (unsigned short)(v >> 16); }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS)
+    nr_encode_packed_kernel(const __grid_constant__ NrGraph g, const signed char* __restrict__ in, long long numCb,
+                            signed char* __restrict__ out, int puncture)
+{
+    extern __shared__ uint32_t esm[];
+    const int Z = g.Z, k = g.ksys, ncore = g.ncore, P = g.P;
+    const int Zh = Z >> 4;                  // 16-bit units per column
+    const int W = (Z + 31) >> 5;            // 32-bit words per column
+    const int DW = ((2 * Z + 31) >> 5) + 2; // words per doubled column (padded)
+    uint32_t* dbl = esm;                            // [ncore][DW]
+    uint32_t* lam = dbl + ncore * DW;               // [4][W]   row sums over the systematic part
+    uint32_t* sum = lam + 4 * W;                    // [DW]     doubled lam0^lam1^lam2^lam3
+    uint32_t* ext = sum + DW;                       // [P-4][W] extension parity
+    const int tid = threadIdx.x;
+    const int firstCol = puncture ? 2 : 0;
+    const int outCols = g.ncols - firstCol;
+    const uint32_t rcpZh = (65536u + Zh - 1) / Zh;  // exact floor(n / Zh) for n < 2730 (n <= 68 * 24)
+    const uint32_t rcpW = (65536u + W - 1) / W;
+    // shifts of the core-parity double diagonal (ldpc.py:1068-1080)
+    int b = edge_shift(g, 1, k);
+    if (b < 0) b = edge_shift(g, 2, k);
+
+    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
+        // ---- load + pack the systematic columns (doubled) ----------------------------------------------------
+        const uint4* src = reinterpret_cast<const uint4*>(in + cb * (long long)k * Z);
+        for (int i = tid; i < ncore * DW + 4 * W + DW; i += ENC_THREADS) esm[i] = 0;
+        __syncthreads();
+        for (int gi = tid; gi < k * Zh; gi += ENC_THREADS) {
+            const uint32_t h = pack16(__ldg(src + gi));
+            const int col = (int)(((uint32_t)gi * rcpZh) >> 16), i = gi - col * Zh;
+            unsigned short* dh = reinterpret_cast<unsigned short*>(dbl + col * DW);
+            dh[i] = (unsigned short)h;
+            dh[i + Zh] = (unsigned short)h;
+        }
+        __syncthreads();
+        // ---- rows 0..3 over the systematic columns ------------------------------------------------------------
+        for (int t = tid; t < 4 * W; t += ENC_THREADS) {
+            const int r = (int)(((uint32_t)t * rcpW) >> 16), i = t - r * W;
+            uint32_t acc = 0;
+            for (int e = g.rowEdge0[r]; e < g.rowEdge0[r + 1]; e++) {
+                const uint32_t ew = g.edge[e];
+                const int col = (int)(ew >> 16);
+                if (col >= k) break;   // columns ascend inside a row
+                acc ^= rot_word(dbl + col * DW, (int)(ew & 0xffffu), i);
+            }
+            lam[r * W + i] = acc;
+        }
+        __syncthreads();
+        if (tid < W) store_doubled(sum, tid, lam[tid] ^ lam[W + tid] ^ lam[2 * W + tid] ^ lam[3 * W + tid], Zh);
+        __syncthreads();
+        // p0 = rot(sum, Z - b)
+        if (tid < W) store_doubled(dbl + k * DW, tid, rot_word(sum, (b == 0) ? 0 : Z - b, tid), Zh);
+        __syncthreads();
+        for (int r = 0; r < 3; r++) {   // p1..p3 through the double diagonal
+            if (tid < W) {
+                uint32_t acc = lam[r * W + tid];
+                for (int e = g.rowEdge0[r]; e < g.rowEdge0[r + 1]; e++) {
+                    const uint32_t ew = g.edge[e];
+                    const int col = (int)(ew >> 16);
+                    if (col >= k && col <= k + r) acc ^= rot_word(dbl + col * DW, (int)(ew & 0xffffu), tid);
+                }
+                store_doubled(dbl + (k + r + 1) * DW, tid, acc, Zh);
+            }
+            __syncthreads();
+        }
+        // ---- extension rows: XOR over the core columns only (ldpc.py:1083-1084) ------------------------------
+        for (int t = tid; t < (P - 4) * W; t += ENC_THREADS) {
+            const int r4 = (int)(((uint32_t)t * rcpW) >> 16), i = t - r4 * W;
+            uint32_t acc = 0;
+            for (int e = g.rowEdge0[r4 + 4]; e < g.rowEdge0[r4 + 5]; e++) {
+                const uint32_t ew = g.edge[e];
+                const int col = (int)(ew >> 16);
+                if (col >= ncore) break;
+                acc ^= rot_word(dbl + col * DW, (int)(ew & 0xffffu), i);
+            }
+            ext[t] = acc;
+        }
+        __syncthreads();
+        // ---- spread to one byte per bit, 16 bytes per store ---------------------------------------------------
+        uint4* dst = reinterpret_cast<uint4*>(out + cb * (long long)outCols * Z);
+        for (int gi = tid; gi < outCols * Zh; gi += ENC_THREADS) {
+            const int oc = (int)(((uint32_t)gi * rcpZh) >> 16), i = gi - oc * Zh;
+            const int col = oc + firstCol;
+            const unsigned short* hp = (col < ncore) ? reinterpret_cast<const unsigned short*>(dbl + col * DW)
+                                                     : reinterpret_cast<const unsigned short*>(ext + (col - ncore) * W);
+            const uint32_t h = hp[i];
+            uint4 v;
+            v.x = spread4(h);
+            v.y = spread4(h >> 4);
+            v.z = spread4(h >> 8);
+            v.w = spread4(h >> 12);
+            dst[gi] = v;
         }
         __syncthreads();
     }
@@ -180,6 +318,16 @@ extern "C" int nrldpc_encode(nrldpc_handle* h, int bg, int zc, const int8_t* cod
     if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
     if (num_cb <= 0) { nr_set_error("encode: bad shape"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
+    if (zc % 16 == 0 && ((uintptr_t)code_blocks & 15) == 0 && ((uintptr_t)coded & 15) == 0 && !getenv("NRLDPC_ENC_BYTEWISE")) {
+        // bit-packed path: vector loads/stores need 16-byte granularity (column length Z is a multiple of 16)
+        const int W = (zc + 31) / 32, DW = (2 * zc + 31) / 32 + 2;
+        const size_t smem = (size_t)(g.ncore * DW + 4 * W + DW + (g.P - 4) * W) * sizeof(uint32_t);
+        const int grid = (int)min((long long)num_cb, (long long)h->numSMs * 16);
+        nr_encode_packed_kernel<<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(g, (const signed char*)code_blocks, num_cb,
+                                                                                  (signed char*)coded, puncture);
+        NR_CUDA_CHECK(cudaGetLastError());
+        return NRLDPC_OK;
+    }
     int cbPerCta = max(1, TX_THREADS / zc);
     if (cbPerCta > num_cb) cbPerCta = (int)num_cb;
     const int nT = (cbPerCta * zc + 31) & ~31;

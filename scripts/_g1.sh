@@ -1,2 +1,6 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['roofline']['kernel_ms'], d['check'])"
+python scripts/bench_kernels.py > gpurun_out/helpers_r2a.json 2>gpurun_out/helpers_r2a.err; python -c "
+import json; d=json.load(open('gpurun_out/helpers_r2a.json'))
+for k,v in d['stages'].items(): print('%-28s %8.3f ms %8.1f GB/s %5.1f%%  %7.1f Mcb/s'%(k,v['ms'],v['GBps'],100*v['frac_of_measured_hbm'],v['Mcb_per_s']))
+"
+tail -3 gpurun_out/helpers_r2a.err
