@@ -109,6 +109,8 @@ extern "C" int nrldpc_create(int device, nrldpc_handle** out)
     h->noTmem = nt ? atoi(nt) : 0;
     const char* ns = getenv("NRLDPC_NO_STATIC_ROWS");
     h->noStaticRows = ns ? atoi(ns) : 0;
+    const char* nst = getenv("NRLDPC_NO_STAGE");
+    h->noStage = nst ? atoi(nst) : 0;
     e = cudaMalloc(&h->workCounter, 16 * sizeof(unsigned int));
     if (e != cudaSuccess) { free(h); nr_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return NRLDPC_ERR_CUDA; }
     cudaMemset(h->workCounter, 0, 16 * sizeof(unsigned int));

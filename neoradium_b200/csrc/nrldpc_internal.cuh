@@ -36,6 +36,7 @@ struct nrldpc_handle {
     int decOcc;             // target resident decoder CTAs per SM (0 = automatic), env NRLDPC_DEC_OCC
     int noStaticRows;       // env NRLDPC_NO_STATIC_ROWS=1: use the dynamic-row decoder kernel everywhere (A/B measurements)
     int noTmem;             // env NRLDPC_NO_TMEM=1: keep the decoder's row state out of Tensor Memory (A/B measurements)
+    int noStage;            // env NRLDPC_NO_STAGE=1: no TMA staging of the rate-matched stream (A/B measurements)
 };
 int nr_reserve_tmp(nrldpc_handle* h, size_t bytes, void** out);
 struct NrGraph;

@@ -25,6 +25,8 @@ __device__ __forceinline__ void step(uint32_t& x, uint32_t a, uint32_t b)
     if (OP == 10) asm volatile("mul.rn.f32 %0, %0, %1;" : "+r"(x) : "r"(a));                 // FMUL
     if (OP == 11) asm volatile("shl.b32 %0, %0, 3;" : "+r"(x));                              // shift by constant (IMAD.SHL or SHF?)
     if (OP == 12) asm volatile("min.f32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));        // FMNMX3
+    if (OP == 14) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; selp.b32 %0, %1, %2, p;}" : "+r"(x) : "r"(a), "r"(b));   // ISETP+SEL
+    if (OP == 15) asm volatile("fma.rn.f32 %0, %0, 0f3F800001, %1;" : "+r"(x) : "r"(a));    // FFMA imm
     if (OP == 13) asm volatile("{.reg .u32 t; mad.lo.u32 t, %0, %1, %2; mad.hi.u32 %0, t, %1, %2;}" : "+r"(x) : "r"(a), "r"(b));   // IMAD + IMAD.HI pair
 }
 
@@ -52,6 +54,54 @@ __global__ void __launch_bounds__(256) mix_kernel(uint32_t* out, uint32_t a, uin
     for (int i = 0; i < NCHAIN; i++) s += x[i] + y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+// packed fp32x2 add / fma (FADD2 / FFMA2): two chains per instruction
+template <int OP>
+__global__ void __launch_bounds__(256) pk_kernel(uint32_t* out, uint32_t a, uint32_t b, long long* cyc)
+{
+    uint32_t x[NCHAIN], y[NCHAIN];
+    for (int i = 0; i < NCHAIN; i++) { x[i] = threadIdx.x + i; y[i] = threadIdx.x * 3 + i; }
+    __syncthreads();
+    for (int it = 0; it < ITERS; it++) {
+#pragma unroll
+        for (int u = 0; u < UNROLL / NCHAIN; u++) {
+#pragma unroll
+            for (int i = 0; i < NCHAIN; i++) {
+                if (OP == 0)
+                    asm volatile("{.reg .b64 p, q; mov.b64 p, {%0, %1}; mov.b64 q, {%2, %3}; add.rn.f32x2 p, p, q; mov.b64 {%0, %1}, p;}"
+                                 : "+r"(x[i]), "+r"(y[i]) : "r"(a), "r"(b));
+                else
+                    asm volatile("{.reg .b64 p, q; mov.b64 p, {%0, %1}; mov.b64 q, {%2, %3}; fma.rn.f32x2 p, p, q, q; mov.b64 {%0, %1}, p;}"
+                                 : "+r"(x[i]), "+r"(y[i]) : "r"(a), "r"(b));
+            }
+        }
+    }
+    uint32_t s = 0;
+    for (int i = 0; i < NCHAIN; i++) s += x[i] + y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int OP>
+void run_pk(const char* name, uint32_t* out, long long* cyc)
+{
+    const int blocks = 148 * 16, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    pk_kernel<OP><<<blocks, threads>>>(out, 0x3f800001u, 0x00000003u, cyc);
+    cudaDeviceSynchronize();
+    cudaEventRecord(e0);
+    pk_kernel<OP><<<blocks, threads>>>(out, 0x3f800001u, 0x00000003u, cyc);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    int clk = 0;
+    cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    const double instr = (double)blocks * (threads / 32) * ITERS * UNROLL;
+    const double cycles = ms * 1e-3 * clk * 1e3;
+    printf("%-28s %.3f warp-instr/clk/SMSP  (%.3f ms)\n", name, instr / cycles / 592.0, ms);
 }
 
 template <int OPA, int OPB, int NB>
@@ -106,6 +156,15 @@ int main()
     run<0, 2, 2>("FADD + 2 IMAD", out, cyc, 3);
     run<5, 4, 1>("FMNMX + 1 LOP3", out, cyc, 2);
     run<7, 4, 1>("SHF + 1 LOP3", out, cyc, 2);
+    run<15, 0, 0>("FFMA imm", out, cyc, 1);
+    run<14, 0, 0>("ISETP+SEL (2 instr)", out, cyc, 2);
+    run<5, 0, 1>("FMNMX + 1 FADD", out, cyc, 2);
+    run<5, 0, 2>("FMNMX + 2 FADD", out, cyc, 3);
+    run<12, 0, 1>("FMNMX3 + 1 FADD", out, cyc, 2);
+    run<4, 1, 1>("LOP3 + 1 FFMA", out, cyc, 2);
+    run<4, 1, 2>("LOP3 + 2 FFMA", out, cyc, 3);
+    run_pk<0>("FADD2 (f32x2)", out, cyc);
+    run_pk<1>("FFMA2 (f32x2)", out, cyc);
     cudaError_t e = cudaGetLastError();
     printf("status: %s\n", cudaGetErrorString(e));
     return 0;
