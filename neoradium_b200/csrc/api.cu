@@ -124,8 +124,22 @@ extern "C" int nrldpc_destroy(nrldpc_handle* h)
     cudaSetDevice(h->device);
     if (h->scratch) cudaFree(h->scratch);
     if (h->tmp) cudaFree(h->tmp);
+    if (h->tmp2) cudaFree(h->tmp2);
     if (h->workCounter) cudaFree(h->workCounter);
     free(h);
+    return NRLDPC_OK;
+}
+
+int nr_reserve_tmp2(nrldpc_handle* h, size_t bytes, void** out)
+{
+    if (bytes > h->tmp2Bytes) {
+        if (h->tmp2) NR_CUDA_CHECK(cudaFree(h->tmp2));
+        h->tmp2 = nullptr;
+        h->tmp2Bytes = 0;
+        NR_CUDA_CHECK(cudaMalloc(&h->tmp2, bytes));
+        h->tmp2Bytes = bytes;
+    }
+    *out = h->tmp2;
     return NRLDPC_OK;
 }
 

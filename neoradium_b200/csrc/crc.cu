@@ -1,94 +1,281 @@
 // K4 (standalone form): CRC attach / check for the six TS 38.212 polynomials, code-block segmentation and
 // CRC-check + merge.  Replaces ChanCodeBase.getCrc/checkCrc/appendCrc (neoradium/chancodebase.py:83-189),
 // LdpcEncoder.doSegmentation (neoradium/ldpc.py:1011-1030) and LdpcDecoder.checkCrcAndMerge (ldpc.py:1610-1619).
-// HBM-bound byte work: one CTA per bit stream, coalesced int8 traffic, per-thread chunk division + log-depth merge.
+// HBM-bound byte work: a warp per stream segment, 8-byte coalesced traffic, bit-packed table-driven CRC (see below).
 #include "crc_device.cuh"
 #include "nrldpc_internal.cuh"
 
 namespace {
 
 constexpr int CRC_THREADS = 256;
+constexpr int CRC_WARPS = CRC_THREADS / 32;
+constexpr int CRC_MAX_SEG = 16384;            // bytes (= bits) of a stream handled by one warp at a time
+constexpr int CRC_MAX_SEGS = 128;             // segments per stream (factor table in shared memory)
 
-struct GlobalBits {
-    const signed char* p;
-    __device__ __forceinline__ uint32_t operator()(long long i) const { return (uint32_t)(p[i] & 1); }
+// ---------------------------------------------------------------------------------------------------------------
+// One kernel for every CRC-carrying byte stream of the chain (getCrc / appendCrc / checkCrc, doSegmentation,
+// checkCrcAndMerge).  A "stream" is `len` values of one bit each (int8, bit = value & 1), optionally zero beyond
+// `avail`.  HBM-bound design:
+//   * a WARP owns one segment of one stream: 8-byte coalesced loads (256 B per request), each lane folds its 8 bytes
+//     into 8 bits with one integer multiply, the same registers are stored to the copy destination (attach /
+//     segmentation / merge move the stream anyway), the packed bits go to a per-warp shared-memory buffer;
+//   * the CRC runs on the PACKED bits: the segment is cut into 32 right-aligned lane chunks, a lane walks its chunk
+//     one packed byte per step through a 256-entry table (rem = (rem << 8) ^ T[top ^ byte]), multiplies its remainder
+//     by x^(bits behind its chunk) (per-lane factor, computed once per kernel) and the lanes XOR-reduce with
+//     redux.sync -- CRC is GF(2)-linear (chancodebase.py:120-128 is the bit-serial form of the same remainder);
+//   * long streams are cut into several segments (work for every SM even with few transport blocks): partial
+//     remainders, already multiplied by x^(bits behind the segment), meet in a global XOR accumulator and the warp
+//     that arrives last writes the result.
+// ---------------------------------------------------------------------------------------------------------------
+enum { BS_CRC = 0, BS_ATTACH = 1, BS_CHECK = 2, BS_SEGMENT = 3, BS_MERGE = 4 };
+
+struct BsArgs {
+    int mode;
+    long long numStreams;
+    long long len;         // bits per stream entering the CRC
+    int segBytes, numSegs; // segmentation of a stream over warps (segBytes multiple of 256)
+    uint32_t poly;
+    int c;
+    int writeCrc;          // BS_SEGMENT: C > 1 (CRC24B appended), else no CRC at all
+    // sources
+    const signed char* src;
+    long long srcStride;   // BS_CRC/ATTACH/CHECK/MERGE: stream s at src + s * srcStride
+    // BS_SEGMENT: stream cb = (t, r) at src + t * srcStride + r * per, valid up to B
+    int C, per, K;
+    long long B;
+    // destinations
+    signed char* dst;      // ATTACH: [s][len + c]; SEGMENT: [cb][K]; MERGE: tbBits
+    long long dstStride;   // MERGE: transport-block pitch
+    signed char* crcBits;  // BS_CRC
+    uint32_t* rem;         // BS_CRC
+    unsigned char* ok;     // BS_CHECK / BS_MERGE
+    // multi-segment combine
+    unsigned int* acc;     // [numStreams] XOR accumulators, zeroed by the host
+    unsigned int* cnt;     // [numStreams] arrival counters, zeroed by the host
+    // GF(2) constants of this call, computed on the host (a few hundred integer operations)
+    uint32_t T[256];                  // T[i] = i(x) * x^c mod g
+    uint32_t laneFac[32];             // x^(8 q (31 - lane)) mod g, q = segBytes / 256 packed bytes per lane chunk
+    uint32_t segFac[CRC_MAX_SEGS];    // x^(bits of the stream behind segment g) mod g
 };
 
-struct PaddedBits {   // transport block zero-extended past its end
-    const signed char* p;
-    long long base, B;
-    __device__ __forceinline__ uint32_t operator()(long long i) const { return (base + i < B) ? (uint32_t)(p[base + i] & 1) : 0u; }
-};
-
-// mode 0: crc bits / remainder; mode 1: attach (copy + crc); mode 2: check
-__global__ void __launch_bounds__(CRC_THREADS)
-    nr_crc_kernel(const signed char* bits, long long numStreams, long long len, long long stride, uint32_t poly, int c,
-                  int mode, signed char* crcBits, uint32_t* rem, signed char* attachOut, unsigned char* ok)
+uint32_t host_gf_mulmod(uint32_t a, uint32_t b, uint32_t poly, int c)
 {
-    __shared__ uint32_t tree[CRC_THREADS];
-    for (long long sidx = blockIdx.x; sidx < numStreams; sidx += gridDim.x) {
-        const signed char* src = bits + sidx * stride;
-        const uint32_t r = nr_group_crc(GlobalBits{src}, len, CRC_THREADS, threadIdx.x, tree, poly, c);
-        if (mode == 1) {
-            signed char* dst = attachOut + sidx * (len + c);
-            for (long long i = threadIdx.x; i < len; i += CRC_THREADS) dst[i] = src[i];
-            if ((int)threadIdx.x < c) dst[len + threadIdx.x] = (signed char)((r >> (c - 1 - threadIdx.x)) & 1u);
-        } else if (mode == 2) {
-            if (threadIdx.x == 0) ok[sidx] = (r == 0);
+    const uint32_t mask = (1u << c) - 1u;
+    uint32_t r = 0;
+    for (int i = c - 1; i >= 0; i--) {
+        const uint32_t top = (r >> (c - 1)) & 1u;
+        r = (r << 1) & mask;
+        if (top) r ^= poly;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r;
+}
+uint32_t host_gf_xpow(long long e, uint32_t poly, int c)
+{
+    uint32_t f = 1, base = host_gf_mulmod(1u, 2u, poly, c);   // x
+    while (e > 0) {
+        if (e & 1) f = host_gf_mulmod(f, base, poly, c);
+        base = host_gf_mulmod(base, base, poly, c);
+        e >>= 1;
+    }
+    return f;
+}
+
+// 8 bytes (one bit each, first byte = first bit of the stream) -> 8 bits, first bit in bit 7
+__device__ __forceinline__ uint32_t pack8(uint2 w)
+{
+    // (w & 0x01010101) * 0x08040201 puts byte0..byte3 into bits 27..24 (no carries: the partial products hit distinct bits)
+    const uint32_t lo = ((w.x & 0x01010101u) * 0x08040201u) >> 24;
+    const uint32_t hi = ((w.y & 0x01010101u) * 0x08040201u) >> 24;
+    return ((lo & 0xFu) << 4) | (hi & 0xFu);
+}
+
+__device__ __forceinline__ uint32_t crc_byte_step(uint32_t rem, uint32_t byte, const uint32_t* T, int c, uint32_t mask)
+{
+    if (c >= 8) return ((rem << 8) & mask) ^ T[((rem >> (c - 8)) ^ byte) & 0xFFu];
+    return T[((rem << (8 - c)) ^ byte) & 0xFFu];   // c < 8: rem * x^8 + byte * x^c = x^c * (rem * x^(8-c) + byte)
+}
+
+__global__ void __launch_bounds__(CRC_THREADS)
+    nr_bitstream_kernel(const __grid_constant__ BsArgs a)
+{
+    __shared__ uint32_t T[256];
+    __shared__ __align__(16) unsigned char pk[CRC_WARPS][CRC_MAX_SEG / 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = a.c;
+    const uint32_t poly = a.poly, mask = (c >= 32) ? 0xFFFFFFFFu : ((1u << c) - 1u);
+    const bool wantCrc = (a.mode != BS_SEGMENT) || a.writeCrc;
+    T[tid] = a.T[tid];   // lane-divergent lookups later: shared memory, not the constant bank
+    const int q = a.segBytes >> 8;                       // packed bytes per lane chunk of a full segment
+    const uint32_t laneFac = a.laneFac[lane];
+    __syncthreads();
+
+    const long long numJobs = a.numStreams * a.numSegs;
+    for (long long job = (long long)blockIdx.x * CRC_WARPS + warp; job < numJobs; job += (long long)gridDim.x * CRC_WARPS) {
+        const long long s = job / a.numSegs;
+        const int g = (int)(job - s * a.numSegs);
+        // geometry of the stream
+        const signed char* src;
+        long long avail = a.len;       // values beyond `avail` are zeros (segmentation pads the transport block)
+        signed char* dst = nullptr;
+        long long copyLen = 0;
+        if (a.mode == BS_SEGMENT) {
+            const long long t = s / a.C;
+            const int r = (int)(s - t * a.C);
+            src = a.src + t * a.srcStride + (long long)r * a.per;
+            avail = max(0LL, min((long long)a.per, a.B - (long long)r * a.per));
+            dst = a.dst + s * (long long)a.K;
+            copyLen = a.per;
         } else {
-            if (crcBits && (int)threadIdx.x < c) crcBits[sidx * c + threadIdx.x] = (signed char)((r >> (c - 1 - threadIdx.x)) & 1u);
-            if (rem && threadIdx.x == 0) rem[sidx] = r;
+            src = a.src + s * a.srcStride;
+            if (a.mode == BS_ATTACH) { dst = a.dst + s * (a.len + c); copyLen = a.len; }
+            if (a.mode == BS_MERGE && a.dst) {
+                const long long t = s / a.C;
+                const int r = (int)(s - t * a.C);
+                dst = a.dst + t * a.dstStride + (long long)r * a.per;
+                copyLen = a.per;
+            }
+        }
+        const long long o0 = (long long)g * a.segBytes;
+        const long long o1 = min(a.len, o0 + a.segBytes);
+        const int nbits = (int)(o1 - o0);
+        const bool srcAligned = ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
+        const bool dstAligned = dst && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+        const bool maskCopy = (a.mode == BS_SEGMENT);   // doSegmentation writes bit values (ldpc.py:1011-1030)
+        // ---- phase 1: load 8 values per lane, copy out, pack ----
+        for (int i = lane * 8; i < nbits; i += 256) {
+            const long long o = o0 + i;
+            uint2 w = make_uint2(0u, 0u);
+            if (srcAligned && o + 8 <= avail) {
+                w = *reinterpret_cast<const uint2*>(src + o);
+            } else {
+                unsigned char* wb = reinterpret_cast<unsigned char*>(&w);
+                for (int k = 0; k < 8; k++)
+                    if (o + k < avail) wb[k] = (unsigned char)src[o + k];
+            }
+            if (dst && o < copyLen) {
+                uint2 wo = w;
+                if (maskCopy) { wo.x &= 0x01010101u; wo.y &= 0x01010101u; }
+                if (dstAligned && o + 8 <= copyLen) {
+                    *reinterpret_cast<uint2*>(dst + o) = wo;
+                } else {
+                    const unsigned char* wb = reinterpret_cast<const unsigned char*>(&wo);
+                    for (int k = 0; k < 8 && o + k < copyLen; k++) dst[o + k] = (signed char)wb[k];
+                }
+            }
+            if (wantCrc) {
+                uint32_t p8 = pack8(w);
+                if (i + 8 > nbits) p8 &= 0xFF00u >> (nbits - i);   // bits beyond the stream end never enter the CRC
+                pk[warp][i >> 3] = (unsigned char)p8;
+            }
+        }
+        if (a.mode == BS_SEGMENT && g == a.numSegs - 1) {
+            // filler bits are zeros (ldpc.py:1026); the CRC bytes (if any) are written by the finishing warp
+            for (int i = a.per + (a.writeCrc ? 24 : 0) + lane; i < a.K; i += 32) dst[i] = 0;
+        }
+        if (!wantCrc) continue;
+        __syncwarp();
+        // ---- phase 2: table-driven CRC over the packed bits, 32 right-aligned lane chunks ----
+        const int nFull = nbits >> 3, tail = nbits & 7;
+        int b0 = nFull - (32 - lane) * q, b1 = b0 + q;
+        b0 = max(b0, 0);
+        uint32_t rem = 0;
+        for (int j = b0; j < b1; j++) rem = crc_byte_step(rem, pk[warp][j], T, c, mask);
+        uint32_t part = (b1 > b0) ? nr_gf_mulmod(rem, laneFac, poly, c) : 0u;
+        part = __reduce_xor_sync(0xffffffffu, part);
+        if (tail) {   // the last (< 8) bits of the stream, bit-serially
+            const uint32_t tb = pk[warp][nFull];
+            for (int k = 0; k < tail; k++) {
+                const uint32_t fb = ((part >> (c - 1)) & 1u) ^ ((tb >> (7 - k)) & 1u);
+                part = (part << 1) & mask;
+                if (fb) part ^= poly;
+            }
+        }
+        __syncwarp();   // pk[warp] is rewritten by the next job
+        // ---- phase 3: combine segments, write the result ----
+        uint32_t R = part;
+        bool finisher = true;
+        if (a.numSegs > 1) {
+            R = nr_gf_mulmod(part, a.segFac[g], poly, c);
+            unsigned int ticket = 0;
+            if (lane == 0) {
+                atomicXor(&a.acc[s], R);
+                __threadfence();
+                ticket = atomicAdd(&a.cnt[s], 1u);
+            }
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            finisher = (ticket == (unsigned int)(a.numSegs - 1));
+            if (finisher) {
+                __threadfence();
+                if (lane == 0) R = atomicXor(&a.acc[s], 0u);
+                R = __shfl_sync(0xffffffffu, R, 0);
+            }
+        }
+        if (!finisher) continue;
+        const signed char bit = (lane < c) ? (signed char)((R >> (c - 1 - lane)) & 1u) : 0;
+        switch (a.mode) {
+            case BS_CRC:
+                if (a.crcBits && lane < c) a.crcBits[s * c + lane] = bit;
+                if (a.rem && lane == 0) a.rem[s] = R;
+                break;
+            case BS_ATTACH:
+                if (lane < c) dst[a.len + lane] = bit;
+                break;
+            case BS_SEGMENT:
+                if (lane < c) dst[a.per + lane] = bit;
+                break;
+            default:   // BS_CHECK, BS_MERGE
+                if (a.ok && lane == 0) a.ok[s] = (R == 0);
+                break;
         }
     }
 }
 
-// doSegmentation: one CTA per code block
-__global__ void __launch_bounds__(CRC_THREADS)
-    nr_segment_kernel(const signed char* tb, long long numTb, long long B, long long tbStride, int C, int K, int per,
-                      signed char* out)
+// segmentation of the streams over warps and launch
+int launch_bitstream(nrldpc_handle* h, BsArgs& a, cudaStream_t st)
 {
-    __shared__ uint32_t tree[CRC_THREADS];
-    const NrCrcPoly pb = nr_crc_poly(NRLDPC_CRC24B);
-    const long long numCb = numTb * C;
-    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
-        const long long t = cb / C;
-        const int r = (int)(cb - t * C);
-        const signed char* src = tb + t * tbStride;
-        const long long base = (long long)r * per;
-        signed char* dst = out + cb * (long long)K;
-        // payload, zero pad at the END of the transport block (ldpc.py:1014-1016)
-        for (int i = threadIdx.x; i < per; i += CRC_THREADS) dst[i] = (base + i < B) ? (signed char)(src[base + i] & 1) : 0;
-        int filled = per;
-        if (C > 1) {
-            const uint32_t rem = nr_group_crc(PaddedBits{src, base, B}, per, CRC_THREADS, threadIdx.x, tree, pb.poly, pb.len);
-            if (threadIdx.x < 24) dst[per + threadIdx.x] = (signed char)((rem >> (23 - threadIdx.x)) & 1u);
-            filled += 24;
-        }
-        for (int i = filled + threadIdx.x; i < K; i += CRC_THREADS) dst[i] = 0;   // filler bits are zeros (ldpc.py:1026)
+    // enough warps for every SM (>= 16 per SM) even with few long streams; a segment is at most CRC_MAX_SEG bytes
+    long long want = ((long long)h->numSMs * 16 + a.numStreams - 1) / a.numStreams;
+    long long segs = max(1LL, min(want, (a.len + 4095) / 4096));
+    segs = max(segs, (a.len + CRC_MAX_SEG - 1) / CRC_MAX_SEG);
+    if (segs > CRC_MAX_SEGS) { nr_set_error("crc: stream of %lld bits is too long", a.len); return NRLDPC_ERR_ARG; }
+    long long seg = (a.len + segs - 1) / segs;
+    seg = max(256LL, (seg + 255) & ~255LL);
+    if (seg > CRC_MAX_SEG) { nr_set_error("crc: stream of %lld bits is too long", a.len); return NRLDPC_ERR_ARG; }
+    a.segBytes = (int)seg;
+    a.numSegs = (int)max(1LL, (a.len + seg - 1) / seg);
+    a.acc = nullptr;
+    a.cnt = nullptr;
+    if (a.numSegs > 1) {
+        void* p = nullptr;
+        const size_t bytes = (size_t)a.numStreams * 2 * sizeof(unsigned int);
+        const int rc = nr_reserve_tmp2(h, bytes, &p);
+        if (rc) return rc;
+        NR_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+        a.acc = (unsigned int*)p;
+        a.cnt = a.acc + a.numStreams;
     }
-}
-
-// checkCrcAndMerge: one CTA per code block
-__global__ void __launch_bounds__(CRC_THREADS)
-    nr_merge_kernel(const signed char* decoded, long long numTb, int C, int K, int F, signed char* tbBits,
-                    long long tbStride, unsigned char* cbOk)
-{
-    __shared__ uint32_t tree[CRC_THREADS];
-    const int Lk = K - F;
-    const int per = (C > 1) ? Lk - 24 : Lk;
-    const NrCrcPoly p = nr_crc_poly(C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
-    const long long numCb = numTb * C;
-    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
-        const signed char* src = decoded + cb * (long long)K;
-        const uint32_t rem = nr_group_crc(GlobalBits{src}, Lk, CRC_THREADS, threadIdx.x, tree, p.poly, p.len);
-        if (cbOk && threadIdx.x == 0) cbOk[cb] = (rem == 0);
-        if (tbBits) {
-            const long long t = cb / C;
-            const int r = (int)(cb - t * C);
-            signed char* dst = tbBits + t * tbStride + (long long)r * per;
-            for (int i = threadIdx.x; i < per; i += CRC_THREADS) dst[i] = src[i];
+    const uint32_t mask = (1u << a.c) - 1u;
+    for (int i = 0; i < 256; i++) {   // i(x) * x^c mod g: the 8 bits of i through the bit-serial divider
+        uint32_t rem = 0;
+        for (int b = 7; b >= 0; b--) {
+            const uint32_t fb = ((rem >> (a.c - 1)) & 1u) ^ (((uint32_t)i >> b) & 1u);
+            rem = (rem << 1) & mask;
+            if (fb) rem ^= a.poly;
         }
+        a.T[i] = rem;
     }
+    const long long q = seg >> 8;
+    for (int l = 0; l < 32; l++) a.laneFac[l] = host_gf_xpow(8LL * q * (31 - l), a.poly, a.c);
+    for (int g = 0; g < a.numSegs; g++) {
+        const long long end = (a.len < (long long)(g + 1) * seg) ? a.len : (long long)(g + 1) * seg;
+        a.segFac[g] = host_gf_xpow(a.len - end, a.poly, a.c);
+    }
+    const long long jobs = a.numStreams * a.numSegs;
+    const int grid = (int)max(1LL, min((jobs + CRC_WARPS - 1) / CRC_WARPS, (long long)h->numSMs * 8));
+    nr_bitstream_kernel<<<grid, CRC_THREADS, 0, st>>>(a);
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
 }
 
 __global__ void nr_counters_kernel(long long numTb, int C, const unsigned char* cbOk, const unsigned char* tbOk,
@@ -139,12 +326,19 @@ int crc_common(nrldpc_handle* h, const int8_t* bits, int64_t n, int64_t len, int
     if (n <= 0 || len < 0 || stride < len) { nr_set_error("crc: bad shape"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
     const NrCrcPoly p = nr_crc_poly(poly);
-    const int grid = (int)min((long long)n, (long long)h->numSMs * 8);
-    nr_crc_kernel<<<grid, CRC_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)bits, n, len, stride, p.poly, p.len,
-                                                                  mode, (signed char*)crcBits, rem,
-                                                                  (signed char*)attachOut, ok);
-    NR_CUDA_CHECK(cudaGetLastError());
-    return NRLDPC_OK;
+    BsArgs a{};
+    a.mode = mode;
+    a.numStreams = n;
+    a.len = len;
+    a.poly = p.poly;
+    a.c = p.len;
+    a.src = (const signed char*)bits;
+    a.srcStride = stride;
+    a.dst = (signed char*)attachOut;
+    a.crcBits = (signed char*)crcBits;
+    a.rem = rem;
+    a.ok = ok;
+    return launch_bitstream(h, a, (cudaStream_t)stream);
 }
 
 }   // namespace
@@ -178,11 +372,22 @@ extern "C" int nrldpc_segment(nrldpc_handle* h, const nrldpc_tb_config* cfg, con
         return NRLDPC_ERR_ARG;
     }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    const int grid = (int)min((long long)num_tb * C, (long long)h->numSMs * 8);
-    nr_segment_kernel<<<grid, CRC_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)tb, num_tb, B, tb_stride, C, K,
-                                                                      (int)per, (signed char*)code_blocks);
-    NR_CUDA_CHECK(cudaGetLastError());
-    return NRLDPC_OK;
+    const NrCrcPoly pb = nr_crc_poly(NRLDPC_CRC24B);
+    BsArgs a{};
+    a.mode = BS_SEGMENT;
+    a.numStreams = num_tb * C;
+    a.len = per;
+    a.poly = pb.poly;
+    a.c = pb.len;
+    a.writeCrc = (C > 1);
+    a.src = (const signed char*)tb;
+    a.srcStride = tb_stride;
+    a.C = C;
+    a.per = (int)per;
+    a.K = K;
+    a.B = B;
+    a.dst = (signed char*)code_blocks;
+    return launch_bitstream(h, a, (cudaStream_t)stream);
 }
 
 extern "C" int nrldpc_check_crc_and_merge(nrldpc_handle* h, const nrldpc_tb_config* cfg, const int8_t* decoded,
@@ -195,12 +400,23 @@ extern "C" int nrldpc_check_crc_and_merge(nrldpc_handle* h, const nrldpc_tb_conf
         return NRLDPC_ERR_ARG;
     }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    const int grid = (int)min((long long)num_tb * cfg->C, (long long)h->numSMs * 8);
-    nr_merge_kernel<<<grid, CRC_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)decoded, num_tb, cfg->C, cfg->K,
-                                                                    cfg->F, (signed char*)tb_bits, tb_bits_stride,
-                                                                    cb_crc_ok);
-    NR_CUDA_CHECK(cudaGetLastError());
-    return NRLDPC_OK;
+    const int Lk = cfg->K - cfg->F;
+    const NrCrcPoly p = nr_crc_poly(cfg->C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
+    BsArgs a{};
+    a.mode = BS_MERGE;
+    a.numStreams = num_tb * cfg->C;
+    a.len = Lk;
+    a.poly = p.poly;
+    a.c = p.len;
+    a.src = (const signed char*)decoded;
+    a.srcStride = cfg->K;
+    a.C = cfg->C;
+    a.per = (cfg->C > 1) ? Lk - 24 : Lk;
+    a.K = cfg->K;
+    a.dst = (signed char*)tb_bits;
+    a.dstStride = tb_bits_stride;
+    a.ok = cb_crc_ok;
+    return launch_bitstream(h, a, (cudaStream_t)stream);
 }
 
 extern "C" int nrldpc_accumulate_counters(nrldpc_handle* h, int64_t num_tb, int C, const uint8_t* cb_crc_ok,

@@ -32,6 +32,8 @@ struct nrldpc_handle {
     unsigned int* workCounter;  // device words: [0] dynamic scheduling counter, [1] last-non-zero-column scan
     void* tmp;              // small per-call temporaries (per-code-block CRC partials), grown on demand
     size_t tmpBytes;
+    void* tmp2;             // second temporary (multi-segment CRC accumulators; may be live together with `tmp`)
+    size_t tmp2Bytes;
     int smemPerSM;
     int decOcc;             // target resident decoder CTAs per SM (0 = automatic), env NRLDPC_DEC_OCC
     int noStaticRows;       // env NRLDPC_NO_STATIC_ROWS=1: use the dynamic-row decoder kernel everywhere (A/B measurements)
@@ -39,6 +41,7 @@ struct nrldpc_handle {
     int noStage;            // env NRLDPC_NO_STAGE=1: no TMA staging of the rate-matched stream (A/B measurements)
 };
 int nr_reserve_tmp(nrldpc_handle* h, size_t bytes, void** out);
+int nr_reserve_tmp2(nrldpc_handle* h, size_t bytes, void** out);
 struct NrGraph;
 // E_r split (getRateMatchedCbLens, ldpc.py:846-856) and k0 (ldpc.py:1145) of a transport-block configuration
 int nr_tb_split(const nrldpc_tb_config* c, int N, int* E0, int* nShort, int* fStep, int* k0);

@@ -253,11 +253,15 @@ __global__ void __launch_bounds__(TX_THREADS)
     }
 }
 
-// rateMatch: one CTA per code block; thread per OUTPUT bit (coalesced stores), gather from the coded block
+// rateMatch (ldpc.py:1128-1159): one CTA per code block.  The first Ncb values of the coded block are staged in shared
+// memory with 16-byte coalesced loads; every thread then produces EIGHT consecutive values of the rate-matched stream
+// (one 8-byte store, groups aligned to the destination address).  The interleaver / circular-buffer index is advanced
+// incrementally inside a group -- one division and two modulos per 8 outputs instead of two of each per output.
 __global__ void __launch_bounds__(256)
     nr_rate_match_kernel(const signed char* coded, long long numCb, int C, int N, int K, int F, int Z, int ncb, int k0,
                          int qm, int E0, int nShort, int fStep, signed char* out, long long outStride)
 {
+    extern __shared__ __align__(16) signed char cbS[];
     const int L = ncb - F;
     const int sysLen = K - 2 * Z - F;
     for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
@@ -268,12 +272,53 @@ __global__ void __launch_bounds__(256)
         const int Eq = E / qm;
         const signed char* src = coded + cb * (long long)N;
         signed char* dst = out + tb * outStride + off;
-        for (int gI = threadIdx.x; gI < E; gI += blockDim.x) {
-            const int sIdx = gI / qm, b = gI - sIdx * qm;   // interleaver: out[s*qm + b] = e[b*Eq + s]  (ldpc.py:1155)
-            const int i = b * Eq + sIdx;
-            const int q = (k0 + i) % L;                      // circular buffer WITHOUT fillers (ldpc.py:1139-1142)
-            const int n = (q < sysLen) ? q : q + F;
-            dst[gI] = src[n];
+        __syncthreads();   // the previous block's gathers are done
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const int n16 = ncb >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(cbS);
+            for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+            for (int i = (n16 << 4) + threadIdx.x; i < ncb; i += blockDim.x) cbS[i] = src[i];
+        } else {
+            for (int i = threadIdx.x; i < ncb; i += blockDim.x) cbS[i] = src[i];
+        }
+        __syncthreads();
+        const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 7);
+        signed char* dstA = dst - mis;                    // 8-byte aligned
+        const int nGroups = (mis + E + 7) >> 3;
+        for (int v = threadIdx.x; v < nGroups; v += blockDim.x) {
+            const int g0 = 8 * v - mis;
+            const int gFirst = max(g0, 0);
+            // interleaver: out[s*qm + b] = e[b*Eq + s] (ldpc.py:1155); e[i] = circ[(k0 + i) mod L], the circular
+            // buffer WITHOUT fillers (ldpc.py:1139-1142)
+            int sIdx = gFirst / qm, b = gFirst - sIdx * qm;
+            int qb0 = (k0 + sIdx) % L;                    // position of (sIdx, b = 0)
+            int q = (int)(((long long)qb0 + (long long)b * Eq) % L);
+            unsigned long long w = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int g = g0 + k;
+                if (g >= 0 && g < E) {
+                    const int n = (q < sysLen) ? q : q + F;
+                    w |= (unsigned long long)(unsigned char)cbS[n] << (8 * k);
+                    if (++b == qm) {
+                        b = 0;
+                        qb0 = (qb0 + 1 == L) ? 0 : qb0 + 1;
+                        q = qb0;
+                    } else {
+                        q += Eq;
+                        while (q >= L) q -= L;
+                    }
+                }
+            }
+            if (g0 >= 0 && g0 + 8 <= E) {
+                *reinterpret_cast<unsigned long long*>(dstA + 8 * v) = w;
+            } else {
+                for (int k = 0; k < 8; k++) {
+                    const int g = g0 + k;
+                    if (g >= 0 && g < E) dst[g] = (signed char)(w >> (8 * k));
+                }
+            }
         }
     }
 }
@@ -375,7 +420,9 @@ extern "C" int nrldpc_rate_match(nrldpc_handle* h, const nrldpc_tb_config* cfg, 
     NR_CUDA_CHECK(cudaSetDevice(h->device));
     const long long numCb = num_tb * cfg->C;
     const int grid = (int)min(numCb, (long long)h->numSMs * 8);
-    nr_rate_match_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const signed char*)coded, numCb, cfg->C, N, cfg->K,
+    const size_t smem = (size_t)((cfg->ncb + 15) & ~15);
+    if (smem > 48 * 1024) NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nr_rate_match_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>((const signed char*)coded, numCb, cfg->C, N, cfg->K,
                                                                  cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, E0, nShort, fStep,
                                                                  (signed char*)out, out_stride);
     NR_CUDA_CHECK(cudaGetLastError());
