@@ -175,6 +175,27 @@ int nrldpc_accumulate_counters(nrldpc_handle* h, int64_t num_tb, int C, const ui
                                const int8_t* ref_bits, int64_t bits_per_tb, int64_t bits_stride, int64_t* counters,
                                nrldpc_stream stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Link around the codec, on the device: the producers of the decoder's input in every NeoRadium
+ * BLER loop.  qm in {1, 2, 4, 6, 8, 10}; symbols are interleaved (re, im) pairs of the given element type.
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Modem.modulate, modulation.py:127-157 (constellation of modulation.py:60-74): bits[num_sym*qm] -> symbols.
+ * Bit-exact: the constellation values are scale * small integer. */
+int nrldpc_modulate(nrldpc_handle* h, int qm, const int8_t* bits, int64_t num_sym, int out_dtype, void* symbols,
+                    nrldpc_stream stream);
+
+/* Modem.getLLRsFromSymbols(symbols, noiseVar, useMax=True), modulation.py:159-204: symbols -> llr[num_sym*qm],
+ * positive => bit 0.  Per-axis search (equal to the reference's 2-D search in exact arithmetic; tolerance in tests). */
+int nrldpc_demap_maxlog(nrldpc_handle* h, int qm, int in_dtype, const void* symbols, int64_t num_sym, double noise_var,
+                        int out_dtype, void* llr, nrldpc_stream stream);
+
+/* Fused modulate -> + CN(0, noise_var) -> max-log LLR in fp32 (what the BLER notebooks do with Modem.modulate,
+ * random.awgn and getLLRsFromSymbols, PDSCH-BLER.ipynb raw lines 117-165).  Noise of symbol n comes from Philox4x32-10
+ * counter (offset + n) under `seed`: independent of launch geometry and of how a sweep is sharded. */
+int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int64_t num_sym, double noise_var, uint64_t seed,
+                    uint64_t offset, float* llr, nrldpc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,9 @@ SIGNATURES = {
                                 _vp, _vp, _vp]),
     "nrldpc_check_crc_and_merge": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nrldpc_accumulate_counters": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "nrldpc_modulate": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
+    "nrldpc_demap_maxlog": (_i32, [_vp, _i32, _i32, _vp, _i64, ctypes.c_double, _i32, _vp, _vp]),
+    "nrldpc_awgn_llr": (_i32, [_vp, _i32, _vp, _i64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
 }
 
 

@@ -1,0 +1,280 @@
+// On-device link around the codec: Gray-mapped QAM of TS 38.211 5.1, complex AWGN and the
+// max-log LLR demapper, so that BLER sweeps and benchmarks never round-trip through the host.
+//
+// Mirrors Modem.modulate / Modem.getLLRsFromSymbols(useMax=True) of neoradium/modulation.py:127-204:
+//   * constellation point of the qm-bit label b0..b(qm-1) (MSB first, modulation.py:64-74): per axis the recursion
+//     a = 2^(q/2) - (1 - 2 b[qm-q]) a for q = 2, 4, .., qm-2 starting from 1, times (1 - 2 b0) [real] or (1 - 2 b1) [imag],
+//     scaled by 1/sqrt(2 | 2 | 10 | 42 | 170 | 682); BPSK puts the same sign on both axes;
+//   * max-log LLR of bit i: (min over points with b_i = 1 of |y - x|^2 - min over points with b_i = 0) / noiseVar, positive => 0.
+//     The reference searches the full 2-D constellation; for these square constellations with independent per-axis Gray
+//     labels the other axis cancels in the difference, so the search here is per axis (2^(qm/2) levels).  Same value
+//     in exact arithmetic, a few ulp apart in floating point (the reference takes |.| by hypot and squares it again):
+//     the parity tests state the tolerance.
+// HBM-bound streaming kernels: a thread owns a group of symbols whose LLRs fill whole 16-byte stores.
+#include <math.h>
+
+#include "nrldpc_internal.cuh"
+
+namespace {
+
+constexpr int LS_THREADS = 256;
+
+__host__ __device__ inline double qam_scale(int qm)
+{
+    switch (qm) {
+        case 1: case 2: return 1.0 / sqrt(2.0);
+        case 4: return 1.0 / sqrt(10.0);
+        case 6: return 1.0 / sqrt(42.0);
+        case 8: return 1.0 / sqrt(170.0);
+        default: return 1.0 / sqrt(682.0);
+    }
+}
+
+// integer amplitudes (re, im) of the label `v` (qm bits, b0 = MSB), modulation.py:64-72
+__device__ __forceinline__ void qam_point(uint32_t v, int qm, int& re, int& im)
+{
+    auto bit = [&](int i) { return (int)((v >> (qm - 1 - i)) & 1u); };
+    re = 1;
+    im = 1;
+    for (int q = 2; q < qm; q += 2) {
+        re = (1 << (q / 2)) - (1 - 2 * bit(qm - q)) * re;
+        im = (1 << (q / 2)) - (1 - 2 * bit(qm + 1 - q)) * im;
+    }
+    re *= 1 - 2 * bit(0);
+    im *= 1 - 2 * bit(qm > 1 ? 1 : 0);
+}
+
+// amplitude of one axis from its `half` label bits (MSB = the sign bit b0 | b1, then outer .. inner)
+__device__ __forceinline__ int pam_level(uint32_t lab, int half)
+{
+    int a = 1;
+    for (int p = half - 1; p >= 1; p--) a = (1 << (half - p)) - (1 - 2 * (int)((lab >> (half - 1 - p)) & 1u)) * a;
+    return (1 - 2 * (int)((lab >> (half - 1)) & 1u)) * a;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(LS_THREADS)
+    nr_modulate_kernel(const signed char* __restrict__ bits, long long numSym, int qm, T* __restrict__ out)
+{
+    const T scale = (T)qam_scale(qm);
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < numSym; s += (long long)gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        for (int i = 0; i < qm; i++) v = (v << 1) | (uint32_t)(bits[s * qm + i] & 1);
+        int re, im;
+        qam_point(v, qm, re, im);
+        out[2 * s] = scale * (T)re;
+        out[2 * s + 1] = scale * (T)im;
+    }
+}
+
+// per-axis max-log LLRs of one received coordinate y: llr[p] for the `half` label bits of the axis
+template <typename T, int MAXH>
+__device__ __forceinline__ void axis_llr(T y, int half, const T* __restrict__ levels, T invN0, T (&llr)[MAXH])
+{
+    T m0[MAXH], m1[MAXH];
+#pragma unroll
+    for (int p = 0; p < MAXH; p++) { m0[p] = (T)INFINITY; m1[p] = (T)INFINITY; }
+    const int nl = 1 << half;
+    for (int l = 0; l < nl; l++) {
+        const T d = y - levels[l];
+        const T d2 = d * d;
+#pragma unroll
+        for (int p = 0; p < MAXH; p++) {
+            if (p < half) {
+                if ((l >> (half - 1 - p)) & 1) m1[p] = fmin(m1[p], d2);
+                else m0[p] = fmin(m0[p], d2);
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < MAXH; p++) llr[p] = (m1[p] - m0[p]) * invN0;
+}
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(LS_THREADS)
+    nr_demap_kernel(const TIn* __restrict__ sym, long long numSym, int qm, double noiseVar, TOut* __restrict__ llr)
+{
+    __shared__ double levels[32];
+    const int half = qm >> 1;
+    if (qm > 1 && (int)threadIdx.x < (1 << half)) levels[threadIdx.x] = qam_scale(qm) * (double)pam_level(threadIdx.x, half);
+    __syncthreads();
+    const double invN0 = 1.0 / noiseVar;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < numSym; s += (long long)gridDim.x * blockDim.x) {
+        const double yr = (double)sym[2 * s], yi = (double)sym[2 * s + 1];
+        if (qm == 1) {
+            // BPSK: points +-(1 + j)/sqrt(2): |y - x1|^2 - |y - x0|^2 = 4 a (yr + yi)
+            const double a = qam_scale(1);
+            const double d0 = (yr - a) * (yr - a) + (yi - a) * (yi - a), d1 = (yr + a) * (yr + a) + (yi + a) * (yi + a);
+            llr[s] = (TOut)((d1 - d0) * invN0);
+            continue;
+        }
+        double lr[5], li[5];
+        axis_llr<double, 5>(yr, half, levels, invN0, lr);
+        axis_llr<double, 5>(yi, half, levels, invN0, li);
+        for (int p = 0; p < half; p++) {
+            llr[s * qm + 2 * p] = (TOut)lr[p];
+            llr[s * qm + 2 * p + 1] = (TOut)li[p];
+        }
+    }
+}
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al., SC'11), written out; one call = four 32-bit words -----------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+// two independent N(0,1) values from two 32-bit words (Box-Muller; u1 in (0,1] keeps the tail to 6.7 sigma)
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b)
+{
+    const float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (a + 0.5) / 2^32
+    const float u2 = (float)b * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    return make_float2(r * cs, r * sn);
+}
+
+// Fused transmit-channel-receive for workload generation: bits -> Gray QAM -> + CN(0, noiseVar) -> max-log LLR (fp32).
+// Symbol n of the call draws its noise from Philox counter (offset + n) under `seed`: the result does not depend on the
+// launch geometry, and a sweep sharded over GPUs / batches stays reproducible by passing the global symbol offset.
+// SPT symbols per thread so that a thread's LLRs fill whole float4 stores.
+template <int QM, int SPT>
+__global__ void __launch_bounds__(LS_THREADS)
+    nr_awgn_llr_kernel(const signed char* __restrict__ bits, long long numSym, float noiseVar, unsigned long long seed,
+                       unsigned long long offset, float* __restrict__ llr)
+{
+    constexpr int HALF = QM / 2;
+    constexpr int NLL = QM * SPT;       // LLRs per thread (multiple of 4 whenever the stream length allows)
+    __shared__ float levels[32];
+    if (QM > 1 && (int)threadIdx.x < (1 << HALF)) levels[threadIdx.x] = (float)qam_scale(QM) * (float)pam_level(threadIdx.x, HALF);
+    __syncthreads();
+    const float scale = (float)qam_scale(QM);
+    const float sigma = sqrtf(0.5f * noiseVar);
+    const float invN0 = 1.0f / noiseVar;
+    const long long numGroups = (numSym + SPT - 1) / SPT;
+    const bool vec = ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && (NLL % 4 == 0);
+    for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < numGroups;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        float o[NLL];
+#pragma unroll
+        for (int k = 0; k < SPT; k++) {
+            const long long s = gidx * SPT + k;
+            if (s < numSym) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int i = 0; i < QM; i++) v = (v << 1) | (uint32_t)(bits[s * QM + i] & 1);
+                int re, im;
+                qam_point(v, QM, re, im);
+                const unsigned long long c = offset + (unsigned long long)s;
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+                const float2 nz = box_muller(rnd.x, rnd.y);
+                const float yr = scale * (float)re + sigma * nz.x, yi = scale * (float)im + sigma * nz.y;
+                if (QM == 1) {
+                    const float a = scale;
+                    const float d0 = (yr - a) * (yr - a) + (yi - a) * (yi - a), d1 = (yr + a) * (yr + a) + (yi + a) * (yi + a);
+                    o[k] = (d1 - d0) * invN0;
+                } else {
+                    float lr[HALF > 0 ? HALF : 1], li[HALF > 0 ? HALF : 1];
+                    axis_llr<float, (HALF > 0 ? HALF : 1)>(yr, HALF, levels, invN0, lr);
+                    axis_llr<float, (HALF > 0 ? HALF : 1)>(yi, HALF, levels, invN0, li);
+#pragma unroll
+                    for (int p = 0; p < HALF; p++) {
+                        o[k * QM + 2 * p] = lr[p];
+                        o[k * QM + 2 * p + 1] = li[p];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < QM; i++) o[k * QM + i] = 0.f;
+            }
+        }
+        const long long base = gidx * NLL;
+        if (vec && (gidx + 1) * SPT <= numSym) {
+#pragma unroll
+            for (int q4 = 0; q4 < NLL / 4; q4++)
+                reinterpret_cast<float4*>(llr + base)[q4] = make_float4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
+        } else {
+            for (int i = 0; i < NLL; i++)
+                if (base + i < numSym * QM) llr[base + i] = o[i];
+        }
+    }
+}
+
+bool qm_ok(int qm) { return qm == 1 || qm == 2 || qm == 4 || qm == 6 || qm == 8 || qm == 10; }
+
+}   // namespace
+
+extern "C" int nrldpc_modulate(nrldpc_handle* h, int qm, const int8_t* bits, int64_t num_sym, int out_dtype, void* symbols,
+                               nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("modulate: null handle"); return NRLDPC_ERR_ARG; }
+    if (!qm_ok(qm) || num_sym <= 0) { nr_set_error("modulate: bad arguments (qm=%d)", qm); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    const int grid = (int)min((num_sym + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);
+    if (out_dtype == NRLDPC_F64)
+        nr_modulate_kernel<double><<<grid, LS_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)bits, num_sym, qm, (double*)symbols);
+    else if (out_dtype == NRLDPC_F32)
+        nr_modulate_kernel<float><<<grid, LS_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)bits, num_sym, qm, (float*)symbols);
+    else { nr_set_error("modulate: bad dtype"); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_demap_maxlog(nrldpc_handle* h, int qm, int in_dtype, const void* symbols, int64_t num_sym,
+                                   double noise_var, int out_dtype, void* llr, nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("demap: null handle"); return NRLDPC_ERR_ARG; }
+    if (!qm_ok(qm) || num_sym <= 0 || !(noise_var > 0.0)) { nr_set_error("demap: bad arguments (qm=%d)", qm); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    const int grid = (int)min((num_sym + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (in_dtype == NRLDPC_F64 && out_dtype == NRLDPC_F64)
+        nr_demap_kernel<double, double><<<grid, LS_THREADS, 0, s>>>((const double*)symbols, num_sym, qm, noise_var, (double*)llr);
+    else if (in_dtype == NRLDPC_F64 && out_dtype == NRLDPC_F32)
+        nr_demap_kernel<double, float><<<grid, LS_THREADS, 0, s>>>((const double*)symbols, num_sym, qm, noise_var, (float*)llr);
+    else if (in_dtype == NRLDPC_F32 && out_dtype == NRLDPC_F64)
+        nr_demap_kernel<float, double><<<grid, LS_THREADS, 0, s>>>((const float*)symbols, num_sym, qm, noise_var, (double*)llr);
+    else if (in_dtype == NRLDPC_F32 && out_dtype == NRLDPC_F32)
+        nr_demap_kernel<float, float><<<grid, LS_THREADS, 0, s>>>((const float*)symbols, num_sym, qm, noise_var, (float*)llr);
+    else { nr_set_error("demap: bad dtype"); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int64_t num_sym, double noise_var,
+                               uint64_t seed, uint64_t offset, float* llr, nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("awgn_llr: null handle"); return NRLDPC_ERR_ARG; }
+    if (!qm_ok(qm) || num_sym <= 0 || !(noise_var > 0.0)) { nr_set_error("awgn_llr: bad arguments (qm=%d)", qm); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const signed char* b = (const signed char*)bits;
+    const float nv = (float)noise_var;
+#define NR_LAUNCH_AWGN(QM, SPT)                                                                               \
+    {                                                                                                          \
+        const long long groups = (num_sym + (SPT)-1) / (SPT);                                                  \
+        const int grid = (int)min((groups + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);          \
+        nr_awgn_llr_kernel<QM, SPT><<<grid, LS_THREADS, 0, s>>>(b, num_sym, nv, seed, offset, llr);            \
+    }
+    switch (qm) {
+        case 1: NR_LAUNCH_AWGN(1, 4) break;
+        case 2: NR_LAUNCH_AWGN(2, 2) break;
+        case 4: NR_LAUNCH_AWGN(4, 1) break;
+        case 6: NR_LAUNCH_AWGN(6, 2) break;
+        case 8: NR_LAUNCH_AWGN(8, 1) break;
+        default: NR_LAUNCH_AWGN(10, 2) break;
+    }
+#undef NR_LAUNCH_AWGN
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}

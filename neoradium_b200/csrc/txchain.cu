@@ -253,6 +253,61 @@ __global__ void __launch_bounds__(TX_THREADS)
     }
 }
 
+// Parity check on bit-packed columns (Z % 16 == 0), same machinery as the packed encoder: the core columns are kept
+// doubled so that a circulant rotation is a funnel shift, the degree-1 extension columns (identity circulant) are read
+// in place.  Syndrome word (row r, word i) = XOR over the row's edges; the block is a code word iff every word is 0.
+__global__ void __launch_bounds__(ENC_THREADS)
+    nr_parity_packed_kernel(const __grid_constant__ NrGraph g, const signed char* __restrict__ coded, long long numCb,
+                            unsigned char* ok)
+{
+    extern __shared__ uint32_t esm[];
+    __shared__ int badFlag;
+    const int Z = g.Z, ncore = g.ncore, P = g.P, ncols = g.ncols;
+    const int Zh = Z >> 4;
+    const int W = (Z + 31) >> 5;
+    const int DW = ((2 * Z + 31) >> 5) + 2;
+    uint32_t* dbl = esm;                  // [ncore][DW] doubled core columns
+    uint32_t* ext = dbl + ncore * DW;     // [P-4][W]    extension columns
+    const int tid = threadIdx.x;
+    const uint32_t rcpZh = (65536u + Zh - 1) / Zh;
+    const uint32_t rcpW = (65536u + W - 1) / W;
+    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
+        const uint4* src = reinterpret_cast<const uint4*>(coded + cb * (long long)ncols * Z);
+        for (int i = tid; i < ncore * DW + (P - 4) * W; i += ENC_THREADS) esm[i] = 0;
+        if (tid == 0) badFlag = 0;
+        __syncthreads();
+        for (int gi = tid; gi < ncols * Zh; gi += ENC_THREADS) {
+            const uint32_t h = pack16(__ldg(src + gi));
+            const int col = (int)(((uint32_t)gi * rcpZh) >> 16), i = gi - col * Zh;
+            if (col < ncore) {
+                unsigned short* dh = reinterpret_cast<unsigned short*>(dbl + col * DW);
+                dh[i] = (unsigned short)h;
+                dh[i + Zh] = (unsigned short)h;
+            } else {
+                reinterpret_cast<unsigned short*>(ext + (col - ncore) * W)[i] = (unsigned short)h;
+            }
+        }
+        __syncthreads();
+        uint32_t any = 0;
+        for (int t = tid; t < P * W; t += ENC_THREADS) {
+            const int r = (int)(((uint32_t)t * rcpW) >> 16), i = t - r * W;
+            uint32_t acc = (r >= 4) ? ext[(r - 4) * W + i] : 0u;
+            for (int e = g.rowEdge0[r]; e < g.rowEdge0[r + 1]; e++) {
+                const uint32_t ew = g.edge[e];
+                const int col = (int)(ew >> 16);
+                if (col >= ncore) break;   // columns ascend inside a row; the extension edge is the identity
+                acc ^= rot_word(dbl + col * DW, (int)(ew & 0xffffu), i);
+            }
+            if (32 * i + 32 > Z) acc &= (1u << (Z - 32 * i)) - 1u;   // bits beyond Z in the last word
+            any |= acc;
+        }
+        if (any) badFlag = 1;
+        __syncthreads();
+        if (tid == 0) ok[cb] = badFlag ? 0 : 1;
+        __syncthreads();
+    }
+}
+
 // rateMatch (ldpc.py:1128-1159): one CTA per code block.  The first Ncb values of the coded block are staged in shared
 // memory with 16-byte coalesced loads; every thread then produces EIGHT consecutive values of the rate-matched stream
 // (one 8-byte store, groups aligned to the destination address).  The interleaver / circular-buffer index is advanced
@@ -393,6 +448,14 @@ extern "C" int nrldpc_parity_check(nrldpc_handle* h, int bg, int zc, const int8_
     if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
     if (num_cb <= 0) { nr_set_error("parity_check: bad shape"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
+    if (zc % 16 == 0 && ((uintptr_t)coded_full & 15) == 0 && !getenv("NRLDPC_ENC_BYTEWISE")) {
+        const int W = (zc + 31) / 32, DW = (2 * zc + 31) / 32 + 2;
+        const size_t smemP = (size_t)(g.ncore * DW + (g.P - 4) * W) * sizeof(uint32_t);
+        const int gridP = (int)min((long long)num_cb, (long long)h->numSMs * 16);
+        nr_parity_packed_kernel<<<gridP, ENC_THREADS, smemP, (cudaStream_t)stream>>>(g, (const signed char*)coded_full, num_cb, ok);
+        NR_CUDA_CHECK(cudaGetLastError());
+        return NRLDPC_OK;
+    }
     int cbPerCta = max(1, TX_THREADS / zc);
     if (cbPerCta > num_cb) cbPerCta = (int)num_cb;
     const int nT = (cbPerCta * zc + 31) & ~31;

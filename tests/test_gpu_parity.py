@@ -379,3 +379,31 @@ def test_error_behaviour_on_gpu():
     assert _native.lib().nrldpc_create(99, ctypes.byref(p)) == _native.ERR_ARG
     with pytest.raises(ValueError):
         _native.check(_native.lib().nrldpc_decode(_dev.handle(), 1, 100, 0, 0, None, 1, 100, 66, 1, 0, 22, None, None, None, None))
+
+
+@pytest.mark.parametrize("bg,zc", [(1, 384), (1, 240), (2, 48), (2, 352), (1, 36), (2, 13), (1, 208)])
+def test_parity_check_detects_single_bit_errors(bg, zc):
+    """nrldpc_parity_check (bit-packed kernel for Zc % 16 == 0, byte-wise otherwise) against the oracle's full-row check:
+    valid code words pass, a single flipped bit anywhere (core, punctured or extension column) fails."""
+    rng = np.random.default_rng(100 * bg + zc)
+    ils = O.set_index_of(zc)
+    k, ncols = (22, 68) if bg == 1 else (10, 52)
+    n_cb = 12
+    cbs = rng.integers(0, 2, (n_cb, k * zc)).astype(np.int8)
+    L, h, s = _native.lib(), _dev.handle(), _dev.stream_ptr()
+    d_cbs = torch.from_numpy(cbs).cuda()
+    full = torch.empty((n_cb, ncols * zc), dtype=torch.int8, device='cuda')
+    _native.check(L.nrldpc_encode(h, bg, zc, _dev.ptr(d_cbs), n_cb, _dev.ptr(full), 0, s))
+    host = full.cpu().numpy()
+    assert np.array_equal(host, O.encode(cbs, bg, zc, ils, puncture=False))
+    flipped = host.copy()
+    pos = [0, zc - 1, zc, k * zc + 5, (k + 4) * zc - 1, (k + 4) * zc, ncols * zc - 1, (ncols - 7) * zc + zc // 2]
+    for i, p in enumerate(pos):
+        flipped[i, p] ^= 1                      # blocks 0..7 carry one error each, 8..11 stay valid
+    ok = torch.empty((n_cb,), dtype=torch.uint8, device='cuda')
+    d_fl = torch.from_numpy(flipped).cuda()
+    _native.check(L.nrldpc_parity_check(h, bg, zc, _dev.ptr(d_fl), n_cb, _dev.ptr(ok), s))
+    got = ok.cpu().numpy().astype(bool)
+    want = np.array([O.parity_ok(flipped[i], bg, zc, ils) for i in range(n_cb)])
+    assert list(want) == [False] * len(pos) + [True] * (n_cb - len(pos))
+    assert list(got) == list(want)
