@@ -181,7 +181,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from neoradium_b200 import LdpcDecoder
-    from neoradium_b200.batch import TbBatchCodec, qam_awgn_llr
+    from neoradium_b200.batch import TbBatchCodec
+    from neoradium_b200.modulation import awgn_llr
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,15 +198,17 @@ def run_ours(args):
     codec = TbBatchCodec(BG, MOD, A, G, precision="fp32", device=dev)
     assert (codec.C, codec.Zc, codec.K, codec.F) == (C_PER_TB, 384, 8448, 0)
 
-    # ---- synthetic inputs: payload -> our TX chain (bit-exact vs the oracle, tests/) -> 16QAM + AWGN -> max-log LLR (fp32)
+    # ---- synthetic inputs: payload -> our TX chain (bit-exact vs the oracle, tests/) -> 16QAM + AWGN -> max-log LLR (fp32),
+    #      all on the device
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
     NB = 4
     payloads, llrs = [], []
-    for _ in range(NB):
+    for b in range(NB):
         pl = torch.randint(0, 2, (tbs, A), dtype=torch.int8, device=dev, generator=gen)
         rm = codec.encode(pl)
-        llrs.append(qam_awgn_llr(rm, QM, SNR_DB, generator=gen, dtype=torch.float32).contiguous())
+        # fused Gray-QAM + AWGN + max-log LLR kernel (nrldpc_awgn_llr), one noise stream per (rank, batch)
+        llrs.append(awgn_llr(rm, QM, snr_db=SNR_DB, seed=SEED + 1000 * rank + b, offset=0))
         payloads.append(pl)
     out = codec.alloc_outputs(tbs)
     torch.cuda.synchronize()

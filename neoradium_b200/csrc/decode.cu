@@ -40,7 +40,7 @@ struct StateStore {
     int tmemRows, smemRows, nT;
     // ALLT: every scheduled row lives in Tensor Memory at a compile-time stride (3 warps per lane quadrant): no tier
     // branches, and with a static row index the TMEM address is base + immediate
-    static constexpr uint32_t kAllTStride = 3u * (sizeof(T) == 4 ? 4u : 8u);
+    static constexpr uint32_t kAllTStride = 3u * (sizeof(T) == 4 ? 4u : 8u);   // referenced by the ALLT instantiations only
     __device__ __forceinline__ void load(int row, RowState<T>& st) const
     {
         if constexpr (ALLT) {

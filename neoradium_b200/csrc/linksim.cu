@@ -220,7 +220,7 @@ extern "C" int nrldpc_modulate(nrldpc_handle* h, int qm, const int8_t* bits, int
     if (!h) { nr_set_error("modulate: null handle"); return NRLDPC_ERR_ARG; }
     if (!qm_ok(qm) || num_sym <= 0) { nr_set_error("modulate: bad arguments (qm=%d)", qm); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    const int grid = (int)min((num_sym + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);
+    const int grid = (int)min((long long)((num_sym + LS_THREADS - 1) / LS_THREADS), (long long)h->numSMs * 16);
     if (out_dtype == NRLDPC_F64)
         nr_modulate_kernel<double><<<grid, LS_THREADS, 0, (cudaStream_t)stream>>>((const signed char*)bits, num_sym, qm, (double*)symbols);
     else if (out_dtype == NRLDPC_F32)
@@ -236,7 +236,7 @@ extern "C" int nrldpc_demap_maxlog(nrldpc_handle* h, int qm, int in_dtype, const
     if (!h) { nr_set_error("demap: null handle"); return NRLDPC_ERR_ARG; }
     if (!qm_ok(qm) || num_sym <= 0 || !(noise_var > 0.0)) { nr_set_error("demap: bad arguments (qm=%d)", qm); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    const int grid = (int)min((num_sym + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);
+    const int grid = (int)min((long long)((num_sym + LS_THREADS - 1) / LS_THREADS), (long long)h->numSMs * 16);
     cudaStream_t s = (cudaStream_t)stream;
     if (in_dtype == NRLDPC_F64 && out_dtype == NRLDPC_F64)
         nr_demap_kernel<double, double><<<grid, LS_THREADS, 0, s>>>((const double*)symbols, num_sym, qm, noise_var, (double*)llr);

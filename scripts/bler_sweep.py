@@ -24,15 +24,23 @@ if world > 1:
 qm = {'QPSK': 2, '16QAM': 4, '64QAM': 6, '256QAM': 8}[args.mod]
 g = int(-(-args.A / args.rate // qm) * qm)
 codec = TbBatchCodec(args.bg, args.mod, args.A, g, precision='fp32', earlyStop=args.early_stop)
-res = []
-for snr in [float(x) for x in args.snrs.split(",")]:
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    d = nd.bler_point(codec, args.tbs, snr, args.iters, seed=int(snr * 100), batch_tbs=256)
-    torch.cuda.synchronize(); d["snr_db"] = snr; d["seconds"] = time.perf_counter() - t0
-    res.append(d)
+from neoradium_b200.sweep import BlerSweep
+sweep = BlerSweep(codec, numIter=args.iters, tbsPerPoint=args.tbs, batchTbs=256, seed=1)
+clock = [time.perf_counter()]
+
+
+def report(d):
+    torch.cuda.synchronize()
+    now = time.perf_counter()
+    d["seconds"] = now - clock[0]
+    clock[0] = now
     if rank == 0:
         print("SNR %.1f dB  TBs %d  BLER %.4f  CB-BLER %.4f  BER %.2e  mean iters %.2f  %.2fs" % (
-            snr, d["txBlocks"], d["bler"], d["cbler"], d["bitErrors"] / (d["txBlocks"] * args.A), d["meanIterations"], d["seconds"]), flush=True)
+            d["snr_db"], d["txBlocks"], d["bler"], d["cbler"], d["bitErrors"] / (d["txBlocks"] * args.A), d["meanIterations"],
+            d["seconds"]), flush=True)
+
+
+res = sweep.run([float(x) for x in args.snrs.split(",")], on_point=report)
 if rank == 0:
     print(json.dumps({"config": vars(args), "world": world, "C": codec.C, "Zc": codec.Zc, "points": res}))
 if world > 1:

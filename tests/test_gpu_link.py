@@ -1,0 +1,94 @@
+"""Parity of the on-device link kernels (csrc/linksim.cu) with the reference modem: `Modem.modulate` bit
+for bit, `Modem.getLLRsFromSymbols` within the stated tolerance (per-axis vs 2-D search: same value in exact
+arithmetic), and the fused modulate -> AWGN -> LLR generator through its noise statistics, its reproducibility and the
+oracle demapper applied to the same noise."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import nr_modem
+from neoradium_b200.modulation import Modem, awgn_llr
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modem_cases.npz"))
+MODS = ["BPSK", "QPSK", "16QAM", "64QAM", "256QAM", "1024QAM"]
+
+
+@pytest.mark.parametrize("mod", MODS)
+def test_modem_against_reference_golden(mod):
+    m = Modem(mod)
+    assert np.array_equal(m.constellation, GOLD[mod + "_constellation"])            # bit-exact complex128
+    sym = m.modulate(GOLD[mod + "_bits"])
+    assert sym.dtype == np.complex128 and np.array_equal(sym, GOLD[mod + "_symbols"])
+    assert np.array_equal(m.modulate(GOLD[mod + "_bits"][1]), GOLD[mod + "_symbols"][1])   # 1-D form
+    n0, ref = float(GOLD[mod + "_n0"]), GOLD[mod + "_llr"]
+    llr = m.getLLRsFromSymbols(GOLD[mod + "_noisy"], n0)
+    assert llr.shape == ref.shape and llr.dtype == np.float64
+    # tolerance: 1e-9 of the LLR scale (distances up to ~|y|^2 / N0 cancel in the difference)
+    scale = np.maximum(1.0, np.abs(ref)) + np.abs(GOLD[mod + "_noisy"]).max() ** 2 / n0
+    assert np.all(np.abs(llr - ref) <= 1e-9 * scale)
+    hard = m.demodulate(GOLD[mod + "_noisy"], n0)
+    sure = np.abs(ref) > 1e-6
+    assert np.array_equal(hard[sure], GOLD[mod + "_hard"][sure])
+    with pytest.raises(ValueError):
+        m.modulate(np.zeros(m.qm + 1, np.int8)) if m.qm > 1 else (_ for _ in ()).throw(ValueError())
+
+
+def test_modem_matches_oracle_on_random_symbols():
+    rng = np.random.default_rng(3)
+    for mod in MODS:
+        qm = nr_modem.QM[mod]
+        y = (rng.standard_normal(500) + 1j * rng.standard_normal(500)) * 0.9
+        n0 = 0.07
+        ref = nr_modem.llrs_maxlog(y, qm, n0)
+        got = Modem(mod).getLLRsFromSymbols(y, n0)
+        assert np.all(np.abs(got - ref) <= 1e-9 * (np.maximum(1.0, np.abs(ref)) + 20 / n0))
+
+
+def _noise_from_qpsk(n_sym, n0, seed, offset=0):
+    """The generator's noise per symbol, recovered exactly from a QPSK run (LLR = 4 a y / N0 per axis, linear in y)."""
+    bits = torch.zeros(n_sym * 2, dtype=torch.int8, device='cuda')
+    llr = awgn_llr(bits, 2, noise_var=n0, seed=seed, offset=offset).cpu().numpy().astype(np.float64).reshape(-1, 2)
+    a = 1 / np.sqrt(2)
+    y = llr * n0 / (4 * a)
+    return (y[:, 0] - a) + 1j * (y[:, 1] - a)
+
+
+def test_awgn_generator_statistics_and_reproducibility():
+    n, n0 = 1 << 20, 0.25
+    z = _noise_from_qpsk(n, n0, seed=11)
+    for comp in (z.real, z.imag):
+        assert abs(comp.mean()) < 4 * np.sqrt(n0 / 2 / n)
+        assert abs(comp.var() / (n0 / 2) - 1) < 0.01
+        k = ((comp / np.sqrt(n0 / 2)) ** 4).mean()
+        assert abs(k - 3) < 0.05                                  # Gaussian kurtosis
+        assert (np.abs(comp) > 4.5 * np.sqrt(n0 / 2)).sum() in range(0, 30)   # expected 7
+    assert abs(np.corrcoef(z.real, z.imag)[0, 1]) < 0.01
+    assert abs(np.corrcoef(z.real[:-1], z.real[1:])[0, 1]) < 0.01
+    # same seed -> same noise; another seed -> different; offset shifts the stream (independent of the launch geometry)
+    assert np.array_equal(z[:4096], _noise_from_qpsk(4096, n0, seed=11))
+    assert not np.array_equal(z[:4096], _noise_from_qpsk(4096, n0, seed=12))
+    assert np.array_equal(z[1000:3000], _noise_from_qpsk(2000, n0, seed=11, offset=1000))
+
+
+@pytest.mark.parametrize("mod,snr", [("BPSK", 1.0), ("QPSK", 4.0), ("16QAM", 10.0), ("64QAM", 16.0), ("256QAM", 22.0), ("1024QAM", 28.0)])
+def test_fused_awgn_llr_equals_oracle_on_the_same_noise(mod, snr):
+    """The noise of symbol k depends on (seed, offset + k) only, not on the modulation: recover it from a QPSK run, apply
+    it to the oracle's symbols and demap with the oracle -- the fused fp32 kernel must agree within fp32 accuracy."""
+    qm = nr_modem.QM[mod]
+    n_sym = 3001                                   # odd: exercises the partial last group of the vector stores
+    rng = np.random.default_rng(qm)
+    bits = rng.integers(0, 2, n_sym * qm).astype(np.int8)
+    n0 = 10.0 ** (-snr / 10)
+    got = awgn_llr(torch.from_numpy(bits).cuda(), qm, snr_db=snr, seed=5, offset=77).cpu().numpy().astype(np.float64)
+    z = _noise_from_qpsk(n_sym, n0, seed=5, offset=77)
+    y = nr_modem.modulate(bits, qm) + z
+    ref = nr_modem.llrs_maxlog(y, qm, n0)
+    tol = 2e-4 * (np.maximum(1.0, np.abs(ref)) + 4.0 / n0 * 0.05)
+    assert np.all(np.abs(got - ref) <= tol), float(np.max(np.abs(got - ref) / tol))
+    # decisions agree wherever the LLR is not within the tolerance of zero
+    sure = np.abs(ref) > 2 * tol
+    assert np.array_equal((got <= 0)[sure], (ref <= 0)[sure])

@@ -1,5 +1,6 @@
 """CPU: the oracle against every golden vector the reference holds for this path (MATLAB 5G Toolbox files of
 Playground/CompareWithMatlab) and against the committed outputs of the unmodified reference (ref_cases.npz)."""
+import os
 import numpy as np
 import pytest
 
@@ -123,3 +124,18 @@ def test_row_skipping_is_exact():
     part = OC.decode_beliefs(llr, bg, zc, ils, 6, np.float32, num_rows=rows)
     ncols = 22 + rows
     assert np.array_equal(full[:, :ncols * zc], part[:, :ncols * zc])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# modem oracle pinned by outputs of the unmodified reference Modem (oracle/gen_golden_modem.py)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mod", ["BPSK", "QPSK", "16QAM", "64QAM", "256QAM", "1024QAM"])
+def test_modem_oracle_matches_reference_outputs(mod):
+    import nr_modem
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modem_cases.npz"))
+    qm = nr_modem.QM[mod]
+    assert np.array_equal(nr_modem.constellation(qm), g[mod + "_constellation"])
+    assert np.array_equal(nr_modem.modulate(g[mod + "_bits"], qm), g[mod + "_symbols"])
+    llr = nr_modem.llrs_maxlog(g[mod + "_noisy"], qm, float(g[mod + "_n0"]))
+    assert np.array_equal(llr, g[mod + "_llr"])
+    assert np.array_equal(np.int8((llr <= 0) * 1), g[mod + "_hard"])
