@@ -7,6 +7,7 @@ include/nrldpc.h.  The operation sequence is the reference's: TX = appendCrc('24
 rateMatch (ldpc.py:1200-1204); RX = recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') (ldpc.py:1234-1251).
 """
 import math
+import os
 
 import torch
 
@@ -82,7 +83,7 @@ class TbBatchCodec:
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decode_host(self, llr_host, numIter, out=None, chunks=4):
+    def decode_host(self, llr_host, numIter, out=None, chunks=None):
         """Host-buffer entry point: llr_host is a float32|float64 [numTb, G'] HOST array (NumPy array or CPU torch
         tensor; pinned memory gives full PCIe speed).  The batch is cut into `chunks` groups of transport blocks and
         pipelined over three CUDA streams -- H2D copy of chunk i+1, fused decode of chunk i and D2H copy of the results of
@@ -93,6 +94,8 @@ class TbBatchCodec:
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(llr_host)
         assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
         numTb, Gp = x.shape
+        if chunks is None:
+            chunks = int(os.environ.get("NRLDPC_HOST_CHUNKS", "4"))
         chunks = max(1, min(int(chunks), numTb))
         bounds = [(numTb * i) // chunks for i in range(chunks + 1)]
         key = (numTb, Gp, x.dtype, chunks)

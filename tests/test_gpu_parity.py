@@ -407,3 +407,48 @@ def test_parity_check_detects_single_bit_errors(bg, zc):
     want = np.array([O.parity_ok(flipped[i], bg, zc, ils) for i in range(n_cb)])
     assert list(want) == [False] * len(pos) + [True] * (n_cb - len(pos))
     assert list(got) == list(want)
+
+
+def test_mixed_slot_256qam_harq_ir_device_soft_buffers():
+    """BASELINE configs[2]: a slot carrying two transport blocks of different base graph / lifting size (256QAM, BG1
+    4 layers R=0.75: C=21; BG2 2 layers R=0.3: C=10, both Zc=384 in the survey's 51-RB allocation, shrunk 4x here so
+    that the oracle stays fast), incremental-redundancy HARQ with the rv sequence [0, 2, 3, 1] of harq.py:376, soft
+    combining in DEVICE-resident buffers (the reference's HarqCW.decBuffer, harq.py:121,169) that never visit the
+    host between transmissions.  Every transmission is checked against the oracle fed with the same LLRs and history:
+    merged bits, CRC flags and the combined soft buffer bit for bit (fp32)."""
+    rng = np.random.default_rng(2026)
+    groups = [dict(bg=1, A=44040, nl=4, rate=0.75, snr=16.5), dict(bg=2, A=9480, nl=2, rate=0.3, snr=8.0)]
+    qm, rvs, n_iter = 8, [0, 2, 3, 1], 6
+    for gcfg in groups:
+        bg, A, nl = gcfg["bg"], gcfg["A"], gcfg["nl"]
+        g = int(np.ceil(A / gcfg["rate"] / (qm * nl))) * qm * nl
+        codecs = {rv: TbBatchCodec(bg, '256QAM', A, g, txLayers=nl, rv=rv, precision='fp32') for rv in set(rvs)}
+        c0 = codecs[0]
+        numTb = 2
+        pl = rng.integers(0, 2, (numTb, A)).astype(np.int8)
+        d_pl = torch.from_numpy(pl).cuda()
+        soft = torch.zeros((numTb * c0.C, c0.ncb - c0.F), dtype=torch.float32, device='cuda')   # decBuffer, on the device
+        obuf = [None] * numTb
+        first_ok = None
+        for k, rv in enumerate(rvs):
+            codec = codecs[rv]
+            rm = codec.encode(d_pl)
+            rm_h = rm.cpu().numpy()
+            llr = np.empty(rm_h.shape, np.float32)
+            for t in range(numTb):
+                assert np.array_equal(rm_h[t], O.tx_chain(pl[t], bg, g, qm, nl, 0, rv)[0])
+                llr[t] = nr_link.qam_awgn_llr(rm_h[t], qm, gcfg["snr"], rng)
+            out = codec.decode(torch.from_numpy(llr).cuda(), n_iter, softBuffer=soft)
+            tb, cbok, tbok = out["tb"].cpu().numpy(), out["cbOk"].cpu().numpy(), out["tbOk"].cpu().numpy()
+            soft_h = soft.cpu().numpy().reshape(numTb, c0.C, -1)
+            for t in range(numTb):
+                rr, obuf[t], p = O.rate_recover(llr[t], A, bg, qm, nl, 0, rv, soft_buffer=obuf[t], dtype=np.float32)
+                assert np.array_equal(soft_h[t], obuf[t]), "soft buffer differs after transmission %d" % k
+                hard = (OC.decode_beliefs(rr, bg, p["Zc"], p["iLS"], n_iter, np.float32)[:, :p["K"]] < 0).astype(np.int8)
+                otb, ocb = O.check_crc_and_merge(hard, p["K"], p["F"], p["C"])
+                assert np.array_equal(tb[t], otb) and list(cbok[t].astype(bool)) == list(ocb)
+                assert bool(tbok[t]) == bool(O.crc_check(otb, '24A'))
+            if k == 0:
+                first_ok = tbok.copy()
+        assert not first_ok.all(), "the first transmission was meant to fail (operating point below the waterfall)"
+        assert tbok.all() and np.array_equal(tb[:, :A], pl), "soft combining of four redundancy versions must decode"
