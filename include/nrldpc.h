@@ -196,6 +196,18 @@ int nrldpc_demap_maxlog(nrldpc_handle* h, int qm, int in_dtype, const void* symb
 int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int64_t num_sym, double noise_var, uint64_t seed,
                     uint64_t offset, float* llr, nrldpc_stream stream);
 
+/* goldSequence(cInit, numBits), utils.py:70-94 (TS 38.211 5.2.1): out[n] = c(n), one int8 per bit.  Generated in
+ * parallel by LFSR jump-ahead; c_init < 2^31. */
+int nrldpc_gold_sequence(nrldpc_handle* h, uint32_t c_init, int64_t num_bits, int8_t* out, nrldpc_stream stream);
+
+/* PDSCH.scrambleBits, pdsch.py:603-608: out = bits ^ c (in place allowed). */
+int nrldpc_scramble_bits(nrldpc_handle* h, uint32_t c_init, const int8_t* bits, int64_t num_bits, int8_t* out,
+                         nrldpc_stream stream);
+
+/* PDSCH.scrambleLLRs, pdsch.py:611-616: out = llrs * (1 - 2 c), dtype NRLDPC_F32 | NRLDPC_F64 (in place allowed). */
+int nrldpc_scramble_llrs(nrldpc_handle* h, uint32_t c_init, int dtype, const void* llrs, int64_t num, void* out,
+                         nrldpc_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

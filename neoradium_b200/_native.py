@@ -122,6 +122,9 @@ SIGNATURES = {
     "nrldpc_modulate": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "nrldpc_demap_maxlog": (_i32, [_vp, _i32, _i32, _vp, _i64, ctypes.c_double, _i32, _vp, _vp]),
     "nrldpc_awgn_llr": (_i32, [_vp, _i32, _vp, _i64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),
+    "nrldpc_gold_sequence": (_i32, [_vp, ctypes.c_uint32, _i64, _vp, _vp]),
+    "nrldpc_scramble_bits": (_i32, [_vp, ctypes.c_uint32, _vp, _i64, _vp, _vp]),
+    "nrldpc_scramble_llrs": (_i32, [_vp, ctypes.c_uint32, _i32, _vp, _i64, _vp, _vp]),
 }
 
 

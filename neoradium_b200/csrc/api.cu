@@ -125,6 +125,8 @@ extern "C" int nrldpc_destroy(nrldpc_handle* h)
     if (h->scratch) cudaFree(h->scratch);
     if (h->tmp) cudaFree(h->tmp);
     if (h->tmp2) cudaFree(h->tmp2);
+    if (h->goldTables) cudaFree(h->goldTables);
+    if (h->crcFacDev) cudaFree(h->crcFacDev);
     if (h->workCounter) cudaFree(h->workCounter);
     free(h);
     return NRLDPC_OK;

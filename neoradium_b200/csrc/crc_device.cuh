@@ -7,14 +7,14 @@
 #pragma once
 #include <stdint.h>
 
-__device__ __forceinline__ uint32_t nr_gf_shift1(uint32_t r, uint32_t poly, int c)
+__host__ __device__ __forceinline__ uint32_t nr_gf_shift1(uint32_t r, uint32_t poly, int c)
 {
     const uint32_t top = (r >> (c - 1)) & 1u;
     r = (r << 1) & ((1u << c) - 1u);
     return top ? (r ^ poly) : r;
 }
 
-__device__ __forceinline__ uint32_t nr_gf_mulmod(uint32_t a, uint32_t b, uint32_t poly, int c)
+__host__ __device__ __forceinline__ uint32_t nr_gf_mulmod(uint32_t a, uint32_t b, uint32_t poly, int c)
 {
     uint32_t r = 0;
     for (int i = c - 1; i >= 0; i--) {
@@ -25,7 +25,7 @@ __device__ __forceinline__ uint32_t nr_gf_mulmod(uint32_t a, uint32_t b, uint32_
 }
 
 // x^e mod g
-__device__ __forceinline__ uint32_t nr_gf_xpow(long long e, uint32_t poly, int c)
+__host__ __device__ __forceinline__ uint32_t nr_gf_xpow(long long e, uint32_t poly, int c)
 {
     uint32_t f = 1, base = nr_gf_shift1(1u, poly, c);   // x (also right when c == 1.. never: c >= 6)
     while (e > 0) {

@@ -23,6 +23,7 @@
 // (no FMA contraction), operation order t = r - old; new = (mag*sign)*0.75; r = t + new, sign(+-0) = +, first-index
 // argmin, the "+100000" second-minimum quirk, clip to +-1e10.  -0.0 inputs are canonicalised to +0.0 at load, which
 // makes the raw sign bit equal to (t < 0) for every t the recursion can produce.
+#include "crc_device.cuh"
 #include "decode_common.cuh"
 
 namespace {
@@ -171,12 +172,12 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const NrCrcPoly polyCb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
     const NrCrcPoly polyA = nr_crc_poly(NRLDPC_CRC24A);
     if (wantCrc) {
-        crc_factors(fac, Lk, Z, P2, polyCb.poly, polyCb.len, tid);
-        if (a.C > 1) crc_factors(fac + 16, per, Z, P2, polyA.poly, polyA.len, tid);
         if (SBG != 0) {
-            __syncthreads();
-            crcFac[tid] = crc_thread_factor(fac, Z, m, polyCb.poly, polyCb.len);
-            if (a.C > 1) crcFac[nT + tid] = crc_thread_factor(fac + 16, Z, m, polyA.poly, polyA.len);
+            crcFac[tid] = a.crcFacDev[tid];
+            crcFac[nT + tid] = a.crcFacDev[nT + tid];
+        } else {
+            crc_factors(fac, Lk, Z, P2, polyCb.poly, polyCb.len, tid);
+            if (a.C > 1) crc_factors(fac + 16, per, Z, P2, polyA.poly, polyA.len, tid);
         }
     }
 
@@ -291,27 +292,25 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 const int nStaged = nCopy - head;
                 int n = m;
                 for (int col = 2; col < lastCol; col++, n += Z) {
-                    T v = (T)0;
-                    if (n < ncb) {
-                        const int nf = n - sysLen;   // >= 0: at or behind the filler gap
-                        if ((unsigned)nf < (unsigned)F) {
-                            v = (T)1e10;             // LARGE_LLR (chancodebase.py:52) after the clip
-                        } else {
-                            int i = n - (nf >= 0 ? F : 0) - k0;
-                            i += (i < 0) ? L : 0;
-                            if (i < E) {
-                                int b = (int)((float)i * rcpEq);   // de-interleaver: stream index (i mod Eq) * qm + i / Eq
-                                int r = i - b * Eq;
-                                if (r >= Eq) { r -= Eq; b++; }
-                                if (r < 0) { r += Eq; b--; }
-                                const int xi = r * qm + b;
-                                if (xi < xAvailI) v = (xi < nStaged) ? (T)sp[xi] : (T)x[xi];
-                                v = FP<T>::mn(v, (T)1e10);   // np.clip(., -1e10, 1e10), ldpc.py:1536
-                                v = FP<T>::mx(v, (T)-1e10);
-                                v = FP<T>::add(v, (T)0);     // -0.0 -> +0.0 (see header)
-                            }
-                        }
-                    }
+                    // branch-free: every thread computes an index, invalid ones read element 0 and drop it
+                    const int nf = n - sysLen;                       // >= 0: at or behind the filler gap
+                    const bool isFill = (unsigned)nf < (unsigned)F;  // LARGE_LLR (chancodebase.py:52) after the clip
+                    int i = n - (nf >= 0 ? F : 0) - k0;
+                    i += (i < 0) ? L : 0;
+                    int b = (int)((float)i * rcpEq);                 // de-interleaver: stream index (i mod Eq) * qm + i / Eq
+                    int r = i - b * Eq;
+                    b += (r >= Eq) ? 1 : 0;
+                    r -= (r >= Eq) ? Eq : 0;
+                    b -= (r < 0) ? 1 : 0;
+                    r += (r < 0) ? Eq : 0;
+                    const int xi = r * qm + b;
+                    const bool valid = (n < ncb) && !isFill && (i < E) && (xi < xAvailI);
+                    T v = (T)sp[(valid && xi < nStaged) ? xi : 0];
+                    if (valid && xi >= nStaged) v = (T)x[xi];        // the (< 4) LLRs behind the last whole 16 bytes
+                    v = FP<T>::mn(v, (T)1e10);                        // np.clip(., -1e10, 1e10), ldpc.py:1536
+                    v = FP<T>::mx(v, (T)-1e10);
+                    v = FP<T>::add(v, (T)0);                          // -0.0 -> +0.0 (see header)
+                    v = valid ? v : ((isFill && n < ncb) ? (T)1e10 : (T)0);
                     if (col < ncore) {
                         rcb[col * Z + m] = v;
                     } else {
@@ -638,6 +637,32 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     a.smemRows = smemRows;
     // TMA staging of the rate-matched stream (fused mode, fp32 stream, no HARQ history): one code block's E LLRs
     a.stageFloats = 0;
+    a.crcFacDev = nullptr;
+    if (staticRows && a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA)) {
+        // per-thread CRC factors (see crc_chunk_product): f_m = x^(B (Z-1-m)) mod g, B = ceil(len / Z)
+        const int Lk = a.K - a.F, per = (a.C > 1) ? Lk - 24 : Lk;
+        const unsigned long long key = ((unsigned long long)(unsigned)Lk << 32) | ((unsigned)Z << 12) | (unsigned)(a.C > 1);
+        if (!h->crcFacDev || h->crcFacKey != key) {
+            if (!h->crcFacDev) NR_CUDA_CHECK(cudaMalloc(&h->crcFacDev, 2 * NR_MAX_Z * sizeof(unsigned int)));
+            unsigned int host[2 * NR_MAX_Z];
+            const NrCrcPoly pc = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A), pa = nr_crc_poly(NRLDPC_CRC24A);
+            for (int which = 0; which < 2; which++) {
+                const NrCrcPoly pp = which ? pa : pc;
+                const int len = which ? per : Lk;
+                const uint32_t base = nr_gf_xpow((len + Z - 1) / Z, pp.poly, pp.len);
+                uint32_t f = 1;
+                for (int m = Z - 1; m >= 0; m--) {
+                    host[which * Z + m] = f;
+                    f = nr_gf_mulmod(f, base, pp.poly, pp.len);
+                }
+            }
+            // the kernel reads [0, nT) and [nT, 2 nT) with nT == Z for the static kernels
+            NR_CUDA_CHECK(cudaMemcpyAsync(h->crcFacDev, host, 2 * Z * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
+            NR_CUDA_CHECK(cudaStreamSynchronize(s));   // `host` is a stack buffer
+            h->crcFacKey = key;
+        }
+        a.crcFacDev = (const unsigned int*)h->crcFacDev;
+    }
     if (staticRows && a.rm && !a.softBuf && !a.inF64 && !h->noStage && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) {
         const int Emax = a.E0 + ((a.nShort < a.C) ? a.fStep : 0);
         const size_t need = (size_t)((Emax + 3 + 3) & ~3) * sizeof(float);

@@ -48,7 +48,10 @@ struct DecArgs {
     void* scratch;
     unsigned int* workCounter;
     // static fp32 kernels: the TMA staging buffer of the fused load phase
-    int stageFloats;    // capacity in floats (multiple of 4); 0 = gather straight from global memory
+    int stageFloats;
+    // fused CRC of the static kernels: per-thread factors x^(B (Z-1-m)) mod g for the code-block CRC [0, Z) and the
+    // CRC24A partial [Z, 2Z); computed on the host once per configuration and cached in the handle
+    const unsigned int* crcFacDev;    // capacity in floats (multiple of 4); 0 = gather straight from global memory
 };
 
 namespace {

@@ -278,3 +278,164 @@ extern "C" int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int
     NR_CUDA_CHECK(cudaGetLastError());
     return NRLDPC_OK;
 }
+
+// =================================================================================================================
+// Scrambling (TS 38.211 5.2.1 / 7.3.1.1): Gold sequence c(n) = x1(n + 1600) ^ x2(n + 1600) and its application to
+// bits (XOR) and LLRs (sign flip).  Mirrors goldSequence (neoradium/utils.py:70-94) and PDSCH.scrambleBits /
+// scrambleLLRs (neoradium/pdsch.py:603-616).
+//
+// The two 31-bit LFSRs advance 31 positions per "word step" (x1 <- A1 x1, x2 <- A2 x2 over GF(2), the same word
+// recurrences the reference iterates); word step 51 holds positions 1581..1611, whose top 12 bits are c(0..11), and every
+// later word holds the next 31 bits of c, LSB first.  The reference walks the words one after the other; here a thread
+// jumps straight to its first word with precomputed powers A^(2^i) (host, constant bank) and then steps through a
+// short run of words, so the sequence is produced in parallel.
+// =================================================================================================================
+namespace {
+
+constexpr int GOLD_POW = 26;          // word steps up to 2^26 (2 Gbit of sequence)
+constexpr int GOLD_WORDS_PER_THREAD = 32;
+
+struct GoldTables {
+    uint32_t a1[GOLD_POW][31];   // column j of A1^(2^i): image of basis vector e_j
+    uint32_t a2[GOLD_POW][31];
+};
+GoldTables g_goldHost;
+bool g_goldReady = false;
+
+inline uint32_t gold_step1(uint32_t x)
+{
+    x ^= (x >> 3);
+    x ^= (x << 28) & 0x7FFFFFFFu;
+    return x;
+}
+inline uint32_t gold_step2(uint32_t x)
+{
+    x ^= (x >> 3) ^ (x >> 2) ^ (x >> 1);
+    x ^= ((x << 28) ^ (x << 29) ^ (x << 30)) & 0x7FFFFFFFu;
+    return x;
+}
+inline uint32_t gold_apply_host(const uint32_t* cols, uint32_t x)
+{
+    uint32_t r = 0;
+    for (int j = 0; j < 31; j++)
+        if ((x >> j) & 1u) r ^= cols[j];
+    return r;
+}
+void gold_build_tables()
+{
+    if (g_goldReady) return;
+    for (int j = 0; j < 31; j++) {
+        g_goldHost.a1[0][j] = gold_step1(1u << j);
+        g_goldHost.a2[0][j] = gold_step2(1u << j);
+    }
+    for (int i = 1; i < GOLD_POW; i++)
+        for (int j = 0; j < 31; j++) {   // A^(2^i) e_j = A^(2^(i-1)) (A^(2^(i-1)) e_j)
+            g_goldHost.a1[i][j] = gold_apply_host(g_goldHost.a1[i - 1], g_goldHost.a1[i - 1][j]);
+            g_goldHost.a2[i][j] = gold_apply_host(g_goldHost.a2[i - 1], g_goldHost.a2[i - 1][j]);
+        }
+    g_goldReady = true;
+}
+
+__device__ __forceinline__ uint32_t gold_apply(const uint32_t* __restrict__ cols, uint32_t x)
+{
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 31; j++) r ^= ((x >> j) & 1u) ? cols[j] : 0u;
+    return r;
+}
+
+// mode 0: out8[n] = c(n); mode 1: out8[n] = bits[n] ^ c(n); mode 2/3: out[n] = llr[n] * (1 - 2 c(n)) (fp32 / fp64)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    nr_gold_kernel(const GoldTables* __restrict__ tab, uint32_t x1w, uint32_t x2w, long long numBits, const void* __restrict__ in,
+                   void* __restrict__ out)
+{
+    // x1w / x2w: LFSR words at word step 51 (host).  Sequence bit n >= 12 sits in word 1 + (n - 12) / 31, bit (n - 12) % 31.
+    __shared__ uint32_t sA1[GOLD_POW * 31], sA2[GOLD_POW * 31];
+    for (int i = threadIdx.x; i < GOLD_POW * 31; i += blockDim.x) {
+        sA1[i] = (&tab->a1[0][0])[i];
+        sA2[i] = (&tab->a2[0][0])[i];
+    }
+    __syncthreads();
+    const long long numWords = 1 + (numBits > 12 ? (numBits - 12 + 30) / 31 : 0);   // word 0 = the 12-bit head
+    const long long numRuns = (numWords + GOLD_WORDS_PER_THREAD - 1) / GOLD_WORDS_PER_THREAD;
+    for (long long run = (long long)blockIdx.x * blockDim.x + threadIdx.x; run < numRuns; run += (long long)gridDim.x * blockDim.x) {
+        const long long w0 = run * GOLD_WORDS_PER_THREAD;
+        uint32_t x1 = x1w, x2 = x2w;
+        for (int i = 0; i < GOLD_POW; i++)
+            if ((w0 >> i) & 1LL) {
+                x1 = gold_apply(sA1 + i * 31, x1);
+                x2 = gold_apply(sA2 + i * 31, x2);
+            }
+        for (int k = 0; k < GOLD_WORDS_PER_THREAD; k++) {
+            const long long w = w0 + k;
+            if (w >= numWords) break;
+            const uint32_t c = x1 ^ x2;
+            // word 0 contributes its bits 19..30 as c(0..11); word w >= 1 its bits 0..30 as c(12 + 31 (w - 1) ..)
+            const long long n0 = (w == 0) ? 0 : 12 + 31 * (w - 1);
+            const int b0 = (w == 0) ? 19 : 0, nb = (w == 0) ? 12 : 31;
+            for (int b = 0; b < nb; b++) {
+                const long long n = n0 + b;
+                if (n >= numBits) break;
+                const uint32_t cb = (c >> (b0 + b)) & 1u;
+                if (MODE == 0) reinterpret_cast<signed char*>(out)[n] = (signed char)cb;
+                if (MODE == 1) reinterpret_cast<signed char*>(out)[n] = (signed char)(reinterpret_cast<const signed char*>(in)[n] ^ (signed char)cb);
+                if (MODE == 2) reinterpret_cast<float*>(out)[n] = cb ? -reinterpret_cast<const float*>(in)[n] : reinterpret_cast<const float*>(in)[n];
+                if (MODE == 3) reinterpret_cast<double*>(out)[n] = cb ? -reinterpret_cast<const double*>(in)[n] : reinterpret_cast<const double*>(in)[n];
+            }
+            x1 ^= (x1 >> 3);
+            x1 ^= (x1 << 28) & 0x7FFFFFFFu;
+            x2 ^= (x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1);
+            x2 ^= ((x2 << 28) ^ (x2 << 29) ^ (x2 << 30)) & 0x7FFFFFFFu;
+        }
+    }
+}
+
+int gold_launch(nrldpc_handle* h, int mode, uint32_t c_init, int64_t num_bits, const void* in, void* out, nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("scramble: null handle"); return NRLDPC_ERR_ARG; }
+    if (num_bits <= 0 || c_init >= 0x80000000u) { nr_set_error("scramble: bad arguments"); return NRLDPC_ERR_ARG; }
+    const long long numWords = 1 + (num_bits > 12 ? (num_bits - 12 + 30) / 31 : 0);
+    if (numWords >= (1LL << GOLD_POW)) { nr_set_error("scramble: sequence too long"); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    gold_build_tables();
+    if (!h->goldTables) {
+        NR_CUDA_CHECK(cudaMalloc(&h->goldTables, sizeof(GoldTables)));
+        NR_CUDA_CHECK(cudaMemcpy(h->goldTables, &g_goldHost, sizeof(GoldTables), cudaMemcpyHostToDevice));
+    }
+    // LFSR words at word step 51 (utils.py:73-78: x1 is the pre-computed constant, x2 comes from cInit)
+    uint32_t x1 = 0x42054D21u, x2 = c_init;
+    for (int i = 0; i < 51; i++) x2 = gold_step2(x2);
+    const long long runs = (numWords + GOLD_WORDS_PER_THREAD - 1) / GOLD_WORDS_PER_THREAD;
+    const int grid = (int)max(1LL, min((runs + 255) / 256, (long long)h->numSMs * 8));
+    const GoldTables* t = (const GoldTables*)h->goldTables;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (mode) {
+        case 0: nr_gold_kernel<0><<<grid, 256, 0, s>>>(t, x1, x2, num_bits, in, out); break;
+        case 1: nr_gold_kernel<1><<<grid, 256, 0, s>>>(t, x1, x2, num_bits, in, out); break;
+        case 2: nr_gold_kernel<2><<<grid, 256, 0, s>>>(t, x1, x2, num_bits, in, out); break;
+        default: nr_gold_kernel<3><<<grid, 256, 0, s>>>(t, x1, x2, num_bits, in, out); break;
+    }
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}
+
+}   // namespace
+
+extern "C" int nrldpc_gold_sequence(nrldpc_handle* h, uint32_t c_init, int64_t num_bits, int8_t* out, nrldpc_stream stream)
+{
+    return gold_launch(h, 0, c_init, num_bits, nullptr, out, stream);
+}
+
+extern "C" int nrldpc_scramble_bits(nrldpc_handle* h, uint32_t c_init, const int8_t* bits, int64_t num_bits, int8_t* out,
+                                    nrldpc_stream stream)
+{
+    return gold_launch(h, 1, c_init, num_bits, bits, out, stream);
+}
+
+extern "C" int nrldpc_scramble_llrs(nrldpc_handle* h, uint32_t c_init, int dtype, const void* llrs, int64_t num, void* out,
+                                    nrldpc_stream stream)
+{
+    if (dtype != NRLDPC_F32 && dtype != NRLDPC_F64) { nr_set_error("scramble_llrs: bad dtype"); return NRLDPC_ERR_ARG; }
+    return gold_launch(h, dtype == NRLDPC_F32 ? 2 : 3, c_init, num, llrs, out, stream);
+}

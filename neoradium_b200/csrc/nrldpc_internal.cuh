@@ -34,6 +34,9 @@ struct nrldpc_handle {
     size_t tmpBytes;
     void* tmp2;             // second temporary (multi-segment CRC accumulators; may be live together with `tmp`)
     size_t tmp2Bytes;
+    void* crcFacDev;        // cached per-thread CRC factors of the fused decoder epilogue (decode.cu), key below
+    unsigned long long crcFacKey;
+    void* goldTables;       // device copy of the Gold-sequence jump tables (linksim.cu), created on first use
     int smemPerSM;
     int decOcc;             // target resident decoder CTAs per SM (0 = automatic), env NRLDPC_DEC_OCC
     int noStaticRows;       // env NRLDPC_NO_STATIC_ROWS=1: use the dynamic-row decoder kernel everywhere (A/B measurements)

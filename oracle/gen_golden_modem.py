@@ -34,6 +34,11 @@ def main():
         d[name + "_n0"] = np.float64(n0)
         d[name + "_llr"] = llr
         d[name + "_hard"] = m.demodulate(noisy, n0)
+    utils = load_reference("utils")
+    for k, (c_init, n) in enumerate([(1, 5), (0x12345, 12), (20001 * (1 << 15) + 1 * (1 << 14) + 17, 13), (777, 43), (778, 44),
+                                     (0x7FFFFFFF, 1000), (0, 200), (4660 * (1 << 15) + 42, 70000)]):
+        d["gold%d_cinit_n" % k] = np.int64([c_init, n])
+        d["gold%d_bits" % k] = np.packbits(np.uint8(utils.goldSequence(c_init, n)))
     np.savez_compressed(OUT, **d)
     print("modem_cases.npz", {k: v.shape for k, v in d.items() if hasattr(v, "shape")})
 

@@ -42,3 +42,38 @@ def llrs_maxlog(symbols, qm, noise_var):
     lls = exponents.max(-2)
     llrs = lls[..., 0, :] - lls[..., 1, :]
     return llrs.reshape(llrs.shape[:-2] + (-1,))
+
+
+def gold_sequence(c_init, num_bits):
+    """goldSequence of neoradium/utils.py:70-94: both 31-bit LFSRs of TS 38.211 5.2.1 advanced one 31-bit word per
+    step; word 51 yields c(0..11) from its 12 top bits, every later word 31 bits LSB first."""
+    x1, x2 = 0x42054D21, int(c_init)
+    for _ in range(51):
+        x2 ^= (x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1)
+        x2 ^= ((x2 << 28) ^ (x2 << 29) ^ (x2 << 30)) & 0x7FFFFFFF
+    c = x1 ^ x2
+    bits = [(c >> i) & 1 for i in range(19, 31)]
+    remaining = num_bits - 12
+    while remaining > 0:
+        x1 ^= x1 >> 3
+        x1 ^= (x1 << 28) & 0x7FFFFFFF
+        x2 ^= (x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1)
+        x2 ^= ((x2 << 28) ^ (x2 << 29) ^ (x2 << 30)) & 0x7FFFFFFF
+        c = x1 ^ x2
+        bits += [(c >> i) & 1 for i in range(31)]
+        remaining -= 31
+    return bits[:num_bits]
+
+
+def gold_sequence_38211(c_init, num_bits):
+    """Independent check: the bit-serial definition of TS 38.211 5.2.1 (Nc = 1600)."""
+    n_total = 1600 + num_bits
+    x1 = [0] * (n_total + 31)
+    x2 = [0] * (n_total + 31)
+    x1[0] = 1
+    for i in range(31):
+        x2[i] = (c_init >> i) & 1
+    for n in range(n_total):
+        x1[n + 31] = (x1[n + 3] + x1[n]) & 1
+        x2[n + 31] = (x2[n + 3] + x2[n + 2] + x2[n + 1] + x2[n]) & 1
+    return [(x1[n + 1600] + x2[n + 1600]) & 1 for n in range(num_bits)]

@@ -92,3 +92,28 @@ def test_fused_awgn_llr_equals_oracle_on_the_same_noise(mod, snr):
     # decisions agree wherever the LLR is not within the tolerance of zero
     sure = np.abs(ref) > 2 * tol
     assert np.array_equal((got <= 0)[sure], (ref <= 0)[sure])
+
+
+def test_gold_sequence_and_scrambling_bit_exact():
+    """goldSequence / scrambleBits / scrambleLLRs (utils.py:70-94, pdsch.py:603-616) against the reference's stored
+    sequences and the oracle: lengths around the 12-bit head and the 31-bit words, and sequences long enough for many
+    threads (each thread jumps to its first LFSR word and walks 32 words)."""
+    from neoradium_b200.scrambling import goldSequence, scramble_, scrambleBits, scrambleLLRs
+    for k in range(8):
+        c_init, n = (int(v) for v in GOLD["gold%d_cinit_n" % k])
+        ref = np.unpackbits(GOLD["gold%d_bits" % k])[:n]
+        got = goldSequence(c_init, n)
+        assert isinstance(got, list) and np.array_equal(np.array(got), ref)
+    rng = np.random.default_rng(9)
+    for c_init, n in [(20001 * (1 << 15) + 17, 1), (5, 11), (6, 12 + 31 * 32), (7, 12 + 31 * 32 + 1), (99, 224640), (12345678, 1000003)]:
+        c = np.array(nr_modem.gold_sequence(c_init, n), dtype=np.int8)
+        assert np.array_equal(np.array(goldSequence(c_init, n), dtype=np.int8), c)
+        bits = rng.integers(0, 2, n).astype(np.int8)
+        sb = scrambleBits(c_init, bits)
+        assert sb.dtype == np.int8 and np.array_equal(sb, bits ^ c)
+        llr = rng.standard_normal(n)
+        sl = scrambleLLRs(c_init, llr)
+        assert sl.dtype == np.float64 and np.array_equal(sl, llr * (1 - 2 * np.float64(c)))
+        d32 = torch.from_numpy(llr.astype(np.float32)).cuda()
+        assert np.array_equal(scramble_(c_init, d32).cpu().numpy(), llr.astype(np.float32) * (1 - 2 * np.float32(c)))
+    assert goldSequence(1, 0) == []

@@ -139,3 +139,14 @@ def test_modem_oracle_matches_reference_outputs(mod):
     llr = nr_modem.llrs_maxlog(g[mod + "_noisy"], qm, float(g[mod + "_n0"]))
     assert np.array_equal(llr, g[mod + "_llr"])
     assert np.array_equal(np.int8((llr <= 0) * 1), g[mod + "_hard"])
+
+
+def test_gold_sequence_oracle_matches_reference_and_38211_definition():
+    import nr_modem
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "modem_cases.npz"))
+    for k in range(8):
+        c_init, n = (int(v) for v in g["gold%d_cinit_n" % k])
+        ref = np.unpackbits(g["gold%d_bits" % k])[:n]
+        assert np.array_equal(np.array(nr_modem.gold_sequence(c_init, n)), ref)
+        if n <= 1000:   # the bit-serial definition of TS 38.211 5.2.1 is slow in Python
+            assert np.array_equal(np.array(nr_modem.gold_sequence_38211(c_init, n)), ref)
