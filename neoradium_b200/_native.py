@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(sp)
                 and os.path.getmtime(obj) > hdr_time):
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NRLDPC_NVCC_EXTRA", "").split() + ["-c", sp, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")

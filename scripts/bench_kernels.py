@@ -46,6 +46,10 @@ stages = {
     "crc_check_24B (CB)": (lambda: _native.check(L.nrldpc_crc_check(h, P(cbs), ncb, 8448, 8448, 4, P(ok), s)), ncb * 8448),
     "parity_check": (lambda: _native.check(L.nrldpc_parity_check(h, 1, 384, P(full), ncb, P(okp), s)), ncb * 68 * 384),
 }
+from neoradium_b200.modulation import awgn_llr
+from neoradium_b200.scrambling import scramble_
+stages["awgn_llr 16QAM (f1)"] = (lambda: awgn_llr(rm, 4, snr_db=9.0, seed=3, out=llr), numTb * G * (1 + 4))
+stages["scramble_llrs f32 (f1)"] = (lambda: scramble_(12345, llr), numTb * G * 8)
 # make inputs meaningful
 stages["crc_attach_24A (TB)"][0](); stages["segment (+CRC24B)"][0](); stages["encode (K2)"][0](); stages["rate_match (K3a)"][0]()
 llr.copy_((1 - 2 * rm.to(torch.float32)) * 3)
