@@ -6,6 +6,9 @@
 #include "nr_bg_tables.h"
 #include "nrldpc_internal.cuh"
 
+#ifndef NR_DEC_PRED_PATH
+#define NR_DEC_PRED_PATH 1   // fp32: predicated FMA-pipe selects in the row body (see sub_sel / twomin_update)
+#endif
 #ifndef NR_DEC_MIN_CTAS
 #define NR_DEC_MIN_CTAS 2   // fp32: cap registers at 80 so that two 384-thread CTAs share an SM
 #endif
@@ -61,7 +64,7 @@ struct __align__(16) NrDecGraph {
     int P, ncols, ksys, ncore, Z;
     uint32_t S;                // ceil(2^32 / Z): lifted positions are tracked as 32-bit fixed-point fractions of Z
     uint32_t one;              // 1, opaque to the compiler: keeps the column-base add an IMAD (FMA pipe) instead of an ALU add
-    int pad[1];
+    float onef;                // 1.0f, opaque to the compiler: an exact register move issued as FMUL on the FMA pipe
     uint16_t rowEdge0[NR_MAX_ROWS + 2];
     uint2 tab[NR_MAX_EDGES];   // x = (shift * S) mod 2^32, y = col*Z*sizeof(T)
 };
@@ -262,6 +265,33 @@ __device__ __forceinline__ void tmem_st(const RowState<double>& st, uint32_t tad
 //   new msg  : every edge gets m1' ^ sign(t) (LOP3, FADD, STS); afterwards the argmin edge alone is re-written with
 //              m2' from the MinSlot record -- no per-edge index compare/select.
 // ---------------------------------------------------------------------------------------------------------------
+
+// fp32 fast path of process_row_at: the two selects of an edge are predicated FMA-pipe instructions instead of ALU-pipe
+// SEL/FMNMX (the kernel is bound by the half-rate ALU pipe, profiles/README.md).
+//   t = rv - x1, or rv - x2 on the edge that received the second minimum in the previous iteration
+__device__ __forceinline__ float sub_sel(float rv, float x1, float x2, uint32_t off, uint32_t oldOff)
+{
+    float t;
+    asm("{.reg .pred p; setp.eq.u32 p, %4, %5; sub.rn.f32 %0, %1, %2; @p sub.rn.f32 %0, %1, %3;}"
+        : "=&f"(t) : "f"(rv), "f"(x1), "f"(x2), "r"(off), "r"(oldOff));
+    return t;
+}
+//   two-min update with the strict first-minimum record: p = |t| < min1;  p: min2 = min1 (exact FMUL by an opaque 1.0f),
+//   record (t, off);  !p: min2 = min(min2, |t|);  min1 = min(min1, |t|).  Equal to min2 = min(min2, max(min1, |t|)) because
+//   min1 <= min2 always.
+__device__ __forceinline__ void twomin_update(uint32_t sa, float t, uint32_t off, float& min1, float& min2, float onef)
+{
+    asm volatile(
+        "{.reg .pred p; .reg .f32 a;\n"
+        "abs.f32 a, %2;\n"
+        "setp.lt.f32 p, a, %0;\n"
+        "@p st.shared.v2.b32 [%3], {%4, %5};\n"
+        "@p mul.rn.f32 %1, %0, %6;\n"
+        "@!p min.f32 %1, %1, a;\n"
+        "min.f32 %0, %0, a;}"
+        : "+f"(min1), "+f"(min2) : "f"(t), "r"(sa), "r"(__float_as_uint(t)), "r"(off), "f"(onef));
+}
+
 __device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32_t ZB, uint32_t one, uint2 tb)
 {
     // (a multiply-high WITH addend needs a zeroed even/odd register pair in SASS: two extra moves per edge)
@@ -286,9 +316,69 @@ __device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_
 
 template <typename T, int D, bool EXT>
 __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* __restrict__ rb, RowState<T>& st,
-                                               uint32_t slot, uint32_t dummyOff)
+                                               uint32_t slot, uint32_t dummyOff, float onef)
 {
     constexpr int OFF_SHIFT = 12;   // EXT rows: D <= 10 sign bits, then the argmin offset
+    if constexpr (sizeof(T) == 4 && NR_DEC_PRED_PATH) {
+        // fp32 state: m1s = alpha*min1 (unsigned), m2s = the SIGNED message of the argmin edge (alpha*min2 * sign),
+        // sw / rext as below.  Same arithmetic as the generic body, value for value.
+        float t[D];
+        const float m1o = st.m1s, x2 = st.m2s;
+        const uint32_t sw = st.sw;
+        const uint32_t oldOff = EXT ? (sw >> OFF_SHIFT) : __float_as_uint(st.rext);
+        float min1 = 0.f, min2 = __int_as_float(0x7f800000);
+        uint32_t nsw = 0;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            float rv;
+            if (EXT && j == D - 1)
+                rv = st.rext;
+            else
+                rv = *reinterpret_cast<const float*>(rb + off[j]);
+            const float x1 = FP<float>::flipbits(m1o, sw << (31 - (D - 1 - j)));
+            t[j] = sub_sel(rv, x1, x2, off[j], oldOff);
+            nsw = __funnelshift_l(__float_as_uint(t[j]), nsw, 1);
+            if (j == 0) {
+                min1 = fabsf(t[j]);
+                slot_init(slot, t[j], off[j]);
+            } else {
+                twomin_update(slot, t[j], off[j], min1, min2, onef);
+            }
+        }
+        const MinSlot<float> best = slot_read(slot, 0.f);
+        min2 = fminf(min2, fabsf(__fadd_rn(best.t, 100000.f)));   // ldpc.py:1563
+        const uint32_t par = __popc(nsw) & 1u;
+        const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;
+        const float m1s = __fmul_rn(min1, 0.75f);
+        const float m2s = __fmul_rn(min2, 0.75f);
+        const float psign = FP<float>::flip(1.f, par);
+        const float m1p = __fmul_rn(m1s, psign), m2p = __fmul_rn(m2s, psign);
+        float rext = 0.f;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const float nv = __fadd_rn(t[j], FP<float>::flipbits(m1p, __float_as_uint(t[j])));
+            if (EXT && j == D - 1)
+                rext = nv;
+            else
+                *reinterpret_cast<float*>(rb + off[j]) = nv;
+        }
+        const float nm2 = FP<float>::flipbits(m2p, __float_as_uint(best.t));   // new message of the argmin edge
+        {
+            const float nv = __fadd_rn(best.t, nm2);
+            *reinterpret_cast<float*>(rb + best.off) = nv;
+            if (EXT) rext = (best.off == dummyOff) ? nv : rext;
+        }
+        st.m1s = m1s;
+        st.m2s = nm2;
+        if (EXT) {
+            st.sw = msw | (best.off << OFF_SHIFT);
+            st.rext = rext;
+        } else {
+            st.sw = msw;
+            st.rext = __uint_as_float(best.off);
+        }
+        return;
+    }
     T t[D];
     T m1s = st.m1s, m2s = st.m2s;
     const uint32_t sw = st.sw;
@@ -359,7 +449,7 @@ __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* _
 {
     uint32_t off[D];
     row_offsets<D, EXT>(g, e0, m, ZB, dummyOff, off);
-    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff);
+    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff, g.onef);
 }
 
 template <typename T>
@@ -468,7 +558,7 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
                                                 RowCtx<T, BG, ROW>& cur)
 {
     constexpr int D = BgRows<BG>::deg(ROW);
-    process_row_at<T, D, (ROW >= 4)>(cur.off, rb, cur.st, slot, dummyOff);
+    process_row_at<T, D, (ROW >= 4)>(cur.off, rb, cur.st, slot, dummyOff, g.onef);
     lb.arrive();
     store.store(ROW, cur.st);
     if constexpr (ROW + 1 < BgRows<BG>::P) {
@@ -622,6 +712,7 @@ void build_dec_graph(const NrGraph& g, NrDecGraph* d)
     d->P = g.P; d->ncols = g.ncols; d->ksys = g.ksys; d->ncore = g.ncore; d->Z = g.Z;
     for (int i = 0; i < NR_MAX_ROWS + 2; i++) d->rowEdge0[i] = g.rowEdge0[i];
     d->one = 1;
+    d->onef = 1.0f;
     d->S = (uint32_t)((0x100000000ULL + (uint64_t)g.Z - 1) / (uint64_t)g.Z);   // ceil(2^32 / Z); Z >= 2
     for (int e = 0; e < g.rowEdge0[g.P]; e++) {
         const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
