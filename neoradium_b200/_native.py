@@ -16,6 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _INCLUDE = os.path.join(_HERE, "..", "include")
 LIB_PATH = os.path.join(_HERE, "libnrldpc.so")
+_LIB_OVERRIDE = os.environ.get("NRLDPC_LIB")   # A/B measurements: load another build of the same library
 _BUILD_DIR = os.path.join(_HERE, "build")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -133,10 +134,10 @@ def lib():
     global _lib
     with _lock:
         if _lib is None:
-            if _stale():
+            if _LIB_OVERRIDE is None and _stale():
                 build()
             try:
-                L = ctypes.CDLL(LIB_PATH)
+                L = ctypes.CDLL(_LIB_OVERRIDE or LIB_PATH)
             except OSError as e:   # no silent fallback
                 raise ImportError("libnrldpc.so could not be loaded (%s); neoradium_b200 has no CPU fallback" % e)
             for name, (res, args) in SIGNATURES.items():

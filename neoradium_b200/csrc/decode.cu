@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     }
     char* rb = reinterpret_cast<char*>(rcb);
     const uint32_t mU = (uint32_t)m;
-    const uint32_t ZB = (uint32_t)Z * (uint32_t)sizeof(T);
+    Lift ZB;
+    ZB.S = g.S;
+    ZB.ZB = (uint32_t)Z * (uint32_t)sizeof(T);
+    ZB.one = g.one;
     const uint32_t dummyOff = (uint32_t)(reinterpret_cast<char*>(dummyW) - rb);
     const int ksys = g.ksys;
 
@@ -156,14 +159,24 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     lb.bar = barLayer;
     lb.phase = 0;
     uint32_t stagePhase = 0;
+    __shared__ uint32_t liftSh[4];
     if (SBG != 0) {
         if (tid == 0) {
+            liftSh[0] = ZB.S;
+            liftSh[1] = ZB.ZB;
+            liftSh[2] = ZB.one;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barLayer), "r"((uint32_t)(nT >> 5)) : "memory");
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barStage), "r"(1u) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
         __syncthreads();
+        if (NR_DEC_LIFT_REGS) {   // per-thread register copies (see struct Lift)
+            const volatile uint32_t* lv = liftSh;
+            ZB.S = lv[0];
+            ZB.ZB = lv[1];
+            ZB.one = lv[2];
+        }
     }
 
     const bool wantCrc = a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA);

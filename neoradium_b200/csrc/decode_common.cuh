@@ -9,6 +9,9 @@
 #ifndef NR_DEC_PRED_PATH
 #define NR_DEC_PRED_PATH 1   // fp32: predicated FMA-pipe selects in the row body (see sub_sel / twomin_update)
 #endif
+#ifndef NR_DEC_LIFT_REGS
+#define NR_DEC_LIFT_REGS 1
+#endif
 #ifndef NR_DEC_MIN_CTAS
 #define NR_DEC_MIN_CTAS 2   // fp32: cap registers at 80 so that two 384-thread CTAs share an SM
 #endif
@@ -292,8 +295,15 @@ __device__ __forceinline__ void twomin_update(uint32_t sa, float t, uint32_t off
         : "+f"(min1), "+f"(min2) : "f"(t), "r"(sa), "r"(__float_as_uint(t)), "r"(off), "f"(onef));
 }
 
-__device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32_t ZB, uint32_t one, uint2 tb)
+// per-thread copies of the three multipliers of lifted_offset.  The static kernels read them back from shared memory
+// once: a value loaded per thread sits in an ordinary register, which lets the edge-table entry be the constant-bank
+// operand of the IMAD (a uniform-register multiplier would force one LDC per edge to fetch the table entry).
+struct Lift {
+    uint32_t S, ZB, one;
+};
+__device__ __forceinline__ uint32_t lifted_offset(uint32_t m, Lift L, uint2 tb)
 {
+    const uint32_t S = L.S, ZB = L.ZB, one = L.one;
     // (a multiply-high WITH addend needs a zeroed even/odd register pair in SASS: two extra moves per edge)
     uint32_t w, p, off;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(w) : "r"(m), "r"(S), "r"(tb.x));
@@ -306,12 +316,11 @@ __device__ __forceinline__ uint32_t lifted_offset(uint32_t m, uint32_t S, uint32
 // points at the thread's dummy word).  Depends on (row, m) only -- the static schedule computes it for the NEXT row
 // between the arrive and the wait of the split layer barrier.
 template <int D, bool EXT>
-__device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_t m, uint32_t ZB, uint32_t dummyOff,
+__device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_t m, Lift ZB, uint32_t dummyOff,
                                             uint32_t (&off)[D])
 {
-    const uint32_t S = g.S, one = g.one;
 #pragma unroll
-    for (int j = 0; j < D; j++) off[j] = (EXT && j == D - 1) ? dummyOff : lifted_offset(m, S, ZB, one, g.tab[e0 + j]);
+    for (int j = 0; j < D; j++) off[j] = (EXT && j == D - 1) ? dummyOff : lifted_offset(m, ZB, g.tab[e0 + j]);
 }
 
 template <typename T, int D, bool EXT>
@@ -445,7 +454,7 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
 
 template <typename T, int D, bool EXT>
 __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t m,
-                                            uint32_t ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff)
+                                            Lift ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff)
 {
     uint32_t off[D];
     row_offsets<D, EXT>(g, e0, m, ZB, dummyOff, off);
@@ -453,7 +462,7 @@ __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* _
 }
 
 template <typename T>
-__device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t m, uint32_t ZB,
+__device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t m, Lift ZB,
                                              RowState<T>& st, uint32_t slot, uint32_t dummyOff)
 {
     const int e0 = g.rowEdge0[row];
@@ -545,7 +554,7 @@ struct RowCtx {   // what a thread prepares for a row before it may touch the po
 };
 
 template <typename T, int BG, int ROW, typename Store>
-__device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, uint32_t ZB, const Store& store,
+__device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift ZB, const Store& store,
                                          uint32_t dummyOff, RowCtx<T, BG, ROW>& c)
 {
     store.load(ROW, c.st);
@@ -553,7 +562,7 @@ __device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, uint32
 }
 
 template <typename T, int BG, int ROW, typename Store>
-__device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, uint32_t ZB,
+__device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
                                                 RowCtx<T, BG, ROW>& cur)
 {
@@ -577,9 +586,9 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
 
 // posterior addressed by edge `e` for lifted index m
 template <typename T>
-__device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t m, uint32_t ZB)
+__device__ __forceinline__ T edge_posterior(const NrDecGraph& g, int e, const char* rb, uint32_t m, Lift ZB)
 {
-    return *reinterpret_cast<const T*>(rb + lifted_offset(m, g.S, ZB, g.one, g.tab[e]));
+    return *reinterpret_cast<const T*>(rb + lifted_offset(m, ZB, g.tab[e]));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
