@@ -159,6 +159,13 @@ def check(rc):
 _handles = {}
 
 
+def new_handle(device_index):
+    """A private library handle (own scratch / temporaries) for work issued concurrently on another stream."""
+    p = _vp()
+    check(lib().nrldpc_create(int(device_index), ctypes.byref(p)))
+    return p
+
+
 def handle(device_index):
     """One library handle per device (the Python layer issues work on torch's current stream)."""
     h = _handles.get(device_index)

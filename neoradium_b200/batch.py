@@ -14,9 +14,26 @@ import torch
 from . import _dev, _native, params
 
 
+class PendingDecode:
+    """Result of ``TbBatchCodec.decode_host(..., wait=False)``: ``result()`` returns the host output dict once the last
+    D2H copy has landed."""
+
+    def __init__(self, hout, event):
+        self._hout, self._event = hout, event
+
+    def done(self):
+        return self._event.query()
+
+    def result(self):
+        self._event.synchronize()
+        return self._hout
+
+
 class TbBatchCodec:
     def __init__(self, baseGraphNo, modulation, txBlockSize, g, txLayers=1, nRef=0, rv=0, precision='fp32',
-                 earlyStop=False, device=None):
+                 earlyStop=False, device=None, ownHandle=False):
+        """``ownHandle=True`` gives the codec a private library handle (scratch, temporaries): required when several
+        codecs issue work concurrently on DIFFERENT streams (include/nrldpc.h: one handle per (device, stream))."""
         if baseGraphNo not in (1, 2):
             raise ValueError("'baseGraphNo' must be 1 or 2!")
         if modulation not in params.MOD_ORDER:
@@ -39,7 +56,8 @@ class TbBatchCodec:
         self.device = device if device is not None else _dev.device()
         self.cfg = _native.TbConfig(bg=self.bg, zc=self.Zc, K=self.K, F=self.F, C=self.C, qm=self.qm, nl=self.nl,
                                     ncb=self.ncb, rv=self.rv, reserved=0, G=self.G)
-        self._h = _native.handle(self.device.index if self.device.index is not None else torch.cuda.current_device())
+        devIdx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._h = _native.new_handle(devIdx) if ownHandle else _native.handle(devIdx)
 
     # ------------------------------------------------------------------------------------------------------------------
     def encode(self, payload):
@@ -83,14 +101,19 @@ class TbBatchCodec:
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decode_host(self, llr_host, numIter, out=None, chunks=None):
+    def decode_host(self, llr_host, numIter, out=None, chunks=None, wait=True, slot=0):
         """Host-buffer entry point: llr_host is a float32|float64 [numTb, G'] HOST array (NumPy array or CPU torch
         tensor; pinned memory gives full PCIe speed).  The batch is cut into `chunks` groups of transport blocks and
         pipelined over three CUDA streams -- H2D copy of chunk i+1, fused decode of chunk i and D2H copy of the results of
         chunk i-1 overlap -- and the call returns after everything has landed on the host.
         `out` (optional) is a dict of preallocated host arrays/tensors {tb, cbOk, tbOk, iters} to write into (NumPy
         `out=` convention; pinned buffers avoid a staging copy); otherwise fresh pinned tensors are allocated.
-        Returns the dict of host torch tensors (use .numpy() for zero-copy views)."""
+        Returns the dict of host torch tensors (use .numpy() for zero-copy views).
+
+        ``wait=False`` returns a ``PendingDecode`` right after the work is queued; its ``result()`` blocks until the
+        outputs are on the host.  Calls queue behind each other on the same three streams, so with two calls in flight
+        (``slot`` 0 / 1 select independent device staging buffers; the caller alternates its host buffers likewise) the
+        H2D copy of the next batch overlaps the decode and D2H of the current one and PCIe never idles."""
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(llr_host)
         assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
         numTb, Gp = x.shape
@@ -99,14 +122,16 @@ class TbBatchCodec:
         chunks = max(1, min(int(chunks), numTb))
         bounds = [(numTb * i) // chunks for i in range(chunks + 1)]
         key = (numTb, Gp, x.dtype, chunks)
-        st = getattr(self, '_pipe', None)
+        if not hasattr(self, '_streams'):
+            self._streams = tuple(torch.cuda.Stream(self.device) for _ in range(3))
+            self._pipe = {}
+        st = self._pipe.get(slot)
         if st is None or st['key'] != key:
-            st = dict(key=key, h2d=torch.cuda.Stream(self.device), comp=torch.cuda.Stream(self.device),
-                      d2h=torch.cuda.Stream(self.device),
+            st = dict(key=key, h2d=self._streams[0], comp=self._streams[1], d2h=self._streams[2],
                       din=[torch.empty((bounds[i + 1] - bounds[i], Gp), dtype=x.dtype, device=self.device)
                            for i in range(chunks)],
                       dout=[self.alloc_outputs(bounds[i + 1] - bounds[i]) for i in range(chunks)])
-            self._pipe = st
+            self._pipe[slot] = st
         if out is None:
             out = dict(tb=torch.empty((numTb, self.C * self.per), dtype=torch.int8).pin_memory(),
                        cbOk=torch.empty((numTb, self.C), dtype=torch.uint8).pin_memory(),
@@ -131,6 +156,11 @@ class TbBatchCodec:
                 st['d2h'].wait_event(ev_done)
                 for k in ('tb', 'cbOk', 'tbOk', 'iters'):
                     hout[k][lo:hi].copy_(st['dout'][i][k], non_blocking=True)
+        if not wait:
+            with torch.cuda.stream(st['d2h']):
+                done = torch.cuda.Event()
+                done.record()
+            return PendingDecode(hout, done)
         st['d2h'].synchronize()
         return hout
 

@@ -293,7 +293,6 @@ extern "C" int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int
 namespace {
 
 constexpr int GOLD_POW = 26;          // word steps up to 2^26 (2 Gbit of sequence)
-constexpr int GOLD_WORDS_PER_THREAD = 32;
 
 struct GoldTables {
     uint32_t a1[GOLD_POW][31];   // column j of A1^(2^i): image of basis vector e_j
@@ -345,49 +344,105 @@ __device__ __forceinline__ uint32_t gold_apply(const uint32_t* __restrict__ cols
 }
 
 // mode 0: out8[n] = c(n); mode 1: out8[n] = bits[n] ^ c(n); mode 2/3: out[n] = llr[n] * (1 - 2 c(n)) (fp32 / fp64)
+//
+// With q = n + 19, sequence bit n is bit q % 31 of LFSR word q / 31 (word 0 = word step 51, whose bits 19..30 are
+// c(0..11)).  A CTA owns a tile of GOLD_TILE consecutive elements: its 256 threads first produce the (<= 2048) words the
+// tile needs into shared memory -- thread t jumps to its first word with the precomputed powers A^(2^i) and steps
+// through 8 words -- and then all threads sweep the tile with 16-byte coalesced accesses, taking their bits from a
+// 62-bit window of two neighbouring words.  HBM-bound: 2 B (bits) / 8 B (fp32) / 16 B (fp64) per element.
+constexpr int GOLD_WPT = 8;                      // words generated per thread per tile
+constexpr int GOLD_TILE = 256 * 246;             // elements per tile: multiple of 16, needs <= 256 * GOLD_WPT - 1 words
+
+__device__ __forceinline__ uint32_t spread4(uint32_t x)   // bits 0..3 -> bytes 0..3
+{
+    return ((x & 0xFu) * 0x00204081u) & 0x01010101u;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
     nr_gold_kernel(const GoldTables* __restrict__ tab, uint32_t x1w, uint32_t x2w, long long numBits, const void* __restrict__ in,
                    void* __restrict__ out)
 {
-    // x1w / x2w: LFSR words at word step 51 (host).  Sequence bit n >= 12 sits in word 1 + (n - 12) / 31, bit (n - 12) % 31.
     __shared__ uint32_t sA1[GOLD_POW * 31], sA2[GOLD_POW * 31];
+    __shared__ uint32_t sW[256 * GOLD_WPT + 1];
     for (int i = threadIdx.x; i < GOLD_POW * 31; i += blockDim.x) {
         sA1[i] = (&tab->a1[0][0])[i];
         sA2[i] = (&tab->a2[0][0])[i];
     }
+    if (threadIdx.x == 0) sW[256 * GOLD_WPT] = 0;
     __syncthreads();
-    const long long numWords = 1 + (numBits > 12 ? (numBits - 12 + 30) / 31 : 0);   // word 0 = the 12-bit head
-    const long long numRuns = (numWords + GOLD_WORDS_PER_THREAD - 1) / GOLD_WORDS_PER_THREAD;
-    for (long long run = (long long)blockIdx.x * blockDim.x + threadIdx.x; run < numRuns; run += (long long)gridDim.x * blockDim.x) {
-        const long long w0 = run * GOLD_WORDS_PER_THREAD;
-        uint32_t x1 = x1w, x2 = x2w;
-        for (int i = 0; i < GOLD_POW; i++)
-            if ((w0 >> i) & 1LL) {
-                x1 = gold_apply(sA1 + i * 31, x1);
-                x2 = gold_apply(sA2 + i * 31, x2);
+    constexpr int V = (MODE == 2) ? 4 : (MODE == 3 ? 2 : 16);   // elements per 16-byte access
+    const long long numTiles = (numBits + GOLD_TILE - 1) / GOLD_TILE;
+    for (long long tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const long long n0 = tile * GOLD_TILE;
+        const long long wFirst = (n0 + 19) / 31;
+        {   // this thread's words wFirst + tid * WPT .. + WPT - 1
+            const long long w0 = wFirst + (long long)threadIdx.x * GOLD_WPT;
+            uint32_t x1 = x1w, x2 = x2w;
+            for (int i = 0; i < GOLD_POW; i++)
+                if ((w0 >> i) & 1LL) {
+                    x1 = gold_apply(sA1 + i * 31, x1);
+                    x2 = gold_apply(sA2 + i * 31, x2);
+                }
+#pragma unroll
+            for (int k = 0; k < GOLD_WPT; k++) {
+                sW[threadIdx.x * GOLD_WPT + k] = x1 ^ x2;
+                x1 ^= (x1 >> 3);
+                x1 ^= (x1 << 28) & 0x7FFFFFFFu;
+                x2 ^= (x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1);
+                x2 ^= ((x2 << 28) ^ (x2 << 29) ^ (x2 << 30)) & 0x7FFFFFFFu;
             }
-        for (int k = 0; k < GOLD_WORDS_PER_THREAD; k++) {
-            const long long w = w0 + k;
-            if (w >= numWords) break;
-            const uint32_t c = x1 ^ x2;
-            // word 0 contributes its bits 19..30 as c(0..11); word w >= 1 its bits 0..30 as c(12 + 31 (w - 1) ..)
-            const long long n0 = (w == 0) ? 0 : 12 + 31 * (w - 1);
-            const int b0 = (w == 0) ? 19 : 0, nb = (w == 0) ? 12 : 31;
-            for (int b = 0; b < nb; b++) {
-                const long long n = n0 + b;
-                if (n >= numBits) break;
-                const uint32_t cb = (c >> (b0 + b)) & 1u;
-                if (MODE == 0) reinterpret_cast<signed char*>(out)[n] = (signed char)cb;
-                if (MODE == 1) reinterpret_cast<signed char*>(out)[n] = (signed char)(reinterpret_cast<const signed char*>(in)[n] ^ (signed char)cb);
-                if (MODE == 2) reinterpret_cast<float*>(out)[n] = cb ? -reinterpret_cast<const float*>(in)[n] : reinterpret_cast<const float*>(in)[n];
-                if (MODE == 3) reinterpret_cast<double*>(out)[n] = cb ? -reinterpret_cast<const double*>(in)[n] : reinterpret_cast<const double*>(in)[n];
-            }
-            x1 ^= (x1 >> 3);
-            x1 ^= (x1 << 28) & 0x7FFFFFFFu;
-            x2 ^= (x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1);
-            x2 ^= ((x2 << 28) ^ (x2 << 29) ^ (x2 << 30)) & 0x7FFFFFFFu;
         }
+        __syncthreads();
+        const uint32_t qBase = (uint32_t)(n0 + 19 - wFirst * 31);   // local position of element n0 (< 31)
+        const long long left = numBits - n0;
+        const int cnt = (int)(left < GOLD_TILE ? left : GOLD_TILE);
+        // V sequence bits starting at local element i (window of two 31-bit words; bit <= 30 leaves >= 32 bits)
+        auto seq_bits = [&](int i) -> uint32_t {
+            const uint32_t q = qBase + (uint32_t)i;
+            const uint32_t w = q / 31u;
+            const uint32_t b = q - w * 31u;
+            const unsigned long long win = (unsigned long long)sW[w] | ((unsigned long long)sW[w + 1] << 31);
+            return (uint32_t)(win >> b);
+        };
+        const bool aligned = ((reinterpret_cast<uintptr_t>(out) | (MODE ? reinterpret_cast<uintptr_t>(in) : 0)) & 15) == 0;
+        if (aligned) {
+            for (int i = threadIdx.x * V; i + V <= cnt; i += 256 * V) {
+                const uint32_t c = seq_bits(i);
+                const long long n = n0 + i;
+                if (MODE == 0 || MODE == 1) {
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (MODE == 1) v = *reinterpret_cast<const uint4*>(reinterpret_cast<const signed char*>(in) + n);
+                    v.x ^= spread4(c);
+                    v.y ^= spread4(c >> 4);
+                    v.z ^= spread4(c >> 8);
+                    v.w ^= spread4(c >> 12);
+                    *reinterpret_cast<uint4*>(reinterpret_cast<signed char*>(out) + n) = v;
+                } else if (MODE == 2) {
+                    uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(in) + n);
+                    v.x ^= (c & 1u) << 31;
+                    v.y ^= (c & 2u) << 30;
+                    v.z ^= (c & 4u) << 29;
+                    v.w ^= (c & 8u) << 28;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<float*>(out) + n) = v;
+                } else {
+                    uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const double*>(in) + n);
+                    v.y ^= (c & 1u) << 31;
+                    v.w ^= (c & 2u) << 30;
+                    *reinterpret_cast<uint4*>(reinterpret_cast<double*>(out) + n) = v;
+                }
+            }
+        }
+        // scalar remainder (tail of the last tile, or everything when a pointer is not 16-byte aligned)
+        for (int i = (aligned ? (cnt / V) * V : 0) + threadIdx.x; i < cnt; i += 256) {
+            const uint32_t cb = seq_bits(i) & 1u;
+            const long long n = n0 + i;
+            if (MODE == 0) reinterpret_cast<signed char*>(out)[n] = (signed char)cb;
+            if (MODE == 1) reinterpret_cast<signed char*>(out)[n] = (signed char)(reinterpret_cast<const signed char*>(in)[n] ^ (signed char)cb);
+            if (MODE == 2) reinterpret_cast<uint32_t*>(out)[n] = reinterpret_cast<const uint32_t*>(in)[n] ^ (cb << 31);
+            if (MODE == 3) reinterpret_cast<unsigned long long*>(out)[n] = reinterpret_cast<const unsigned long long*>(in)[n] ^ ((unsigned long long)cb << 63);
+        }
+        __syncthreads();   // sW is rewritten by the next tile
     }
 }
 
@@ -406,8 +461,8 @@ int gold_launch(nrldpc_handle* h, int mode, uint32_t c_init, int64_t num_bits, c
     // LFSR words at word step 51 (utils.py:73-78: x1 is the pre-computed constant, x2 comes from cInit)
     uint32_t x1 = 0x42054D21u, x2 = c_init;
     for (int i = 0; i < 51; i++) x2 = gold_step2(x2);
-    const long long runs = (numWords + GOLD_WORDS_PER_THREAD - 1) / GOLD_WORDS_PER_THREAD;
-    const int grid = (int)max(1LL, min((runs + 255) / 256, (long long)h->numSMs * 8));
+    const long long tiles = (num_bits + GOLD_TILE - 1) / GOLD_TILE;
+    const int grid = (int)max(1LL, min(tiles, (long long)h->numSMs * 4));
     const GoldTables* t = (const GoldTables*)h->goldTables;
     cudaStream_t s = (cudaStream_t)stream;
     switch (mode) {

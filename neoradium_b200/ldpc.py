@@ -266,6 +266,19 @@ class LdpcEncoder(LdpcBase):
 
 
 # **********************************************************************************************************************
+class _PendingLLRs:
+    """Result of ``LdpcDecoder.decodeLLRsAsync``; ``result()`` blocks until the outputs are on the host."""
+
+    def __init__(self, pend, unpack):
+        self._pend, self._unpack = pend, unpack
+
+    def done(self):
+        return self._pend.done()
+
+    def result(self):
+        return self._unpack(self._pend.result())
+
+
 class LdpcDecoder(LdpcBase):
     """LDPC decoder: rate recovery, layered min-sum decoding, CRC check and merge (neoradium/ldpc.py:1220-1619)."""
 
@@ -380,7 +393,18 @@ class LdpcDecoder(LdpcBase):
         return tbBits, okHost
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decodeLLRs(self, llrs, txBlockSize, numIter=5, harq=None, precision=None, returnDevice=False, out=None):
+    def decodeLLRsAsync(self, llrs, txBlockSize, numIter=5, out=None, slot=0):
+        """Non-blocking ``decodeLLRs`` for a [numTb, G] HOST batch (extension): queues the H2D copies, the fused decode
+        and the D2H copies and returns a pending result (``.result()`` -> (txBlocks, cbCrc, tbCrc)).  Keep at most two
+        calls in flight, alternating ``slot`` 0/1 and the (pinned) host input/output buffers: the next batch's H2D
+        then overlaps the current batch's decode and D2H."""
+        isT = isinstance(llrs, torch.Tensor)
+        if (llrs.dim() if isT else np.ndim(llrs)) != 2 or (isT and llrs.device.type != 'cpu'):
+            raise ValueError("decodeLLRsAsync takes a [numTb, G] host batch")
+        return self.decodeLLRs(llrs, txBlockSize, numIter, out=out, _async=int(slot))
+
+    def decodeLLRs(self, llrs, txBlockSize, numIter=5, harq=None, precision=None, returnDevice=False, out=None,
+                   _async=None):
         """Fused RX chain (extension; the operation sequence of HarqCW.decodeLLRs, harq.py:165-173):
         recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') in one kernel pass.
 
@@ -391,6 +415,8 @@ class LdpcDecoder(LdpcBase):
         as in ``recoverRate``.  A [numTb, G] HOST batch takes the pipelined path (``TbBatchCodec.decode_host``: chunked
         H2D / decode / D2H overlap); ``out`` may then carry preallocated (ideally pinned) host arrays
         {tb [numTb, C*per], cbOk [numTb, C], tbOk [numTb], iters [numTb, C]} that receive the results."""
+        if _async is not None:
+            assert harq is None and not returnDevice
         self._rx_setup(txBlockSize)
         c, z = self.numCodeBlocks, self.liftingSize
         precision = precision or self.precision
@@ -408,10 +434,14 @@ class LdpcDecoder(LdpcBase):
                 codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, x.shape[1], self.txLayers, self.nRef,
                                      0, precision, self.earlyStop)
                 self._hostCodec, self._hostCodecKey = codec, key
-            res = codec.decode_host(x, numIter, out=out)
-            self.lastIterations = res['iters'].numpy().reshape(-1)
-            return (res['tb'].numpy()[:, :txBlockSize], res['cbOk'].numpy().view(np.bool_),
-                    res['tbOk'].numpy().view(np.bool_))
+            def unpack(res):
+                self.lastIterations = res['iters'].numpy().reshape(-1)
+                return (res['tb'].numpy()[:, :txBlockSize], res['cbOk'].numpy().view(np.bool_),
+                        res['tbOk'].numpy().view(np.bool_))
+            if _async is not None:
+                pend = codec.decode_host(x, numIter, out=out, wait=False, slot=_async)
+                return _PendingLLRs(pend, unpack)
+            return unpack(codec.decode_host(x, numIter, out=out))
         x = _dev.to_dev(llrs)
         if x.dtype not in (torch.float32, torch.float64):
             x = x.to(torch.float64)

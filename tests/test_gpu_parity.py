@@ -452,3 +452,53 @@ def test_mixed_slot_256qam_harq_ir_device_soft_buffers():
                 first_ok = tbok.copy()
         assert not first_ok.all(), "the first transmission was meant to fail (operating point below the waterfall)"
         assert tbok.all() and np.array_equal(tb[:, :A], pl), "soft combining of four redundancy versions must decode"
+
+
+def test_async_host_batches_and_concurrent_codecs():
+    """Two host batches in flight (decodeLLRsAsync, alternating slots) and two codecs with private handles on two streams
+    give exactly the results of the blocking single-stream calls, which equal the oracle's (low SNR: some blocks fail)."""
+    bg, A, mod, qm, numTb = 1, 8424 * 3 - 24, '16QAM', 4, 6
+    g = 14040 * 3
+    rng = np.random.default_rng(77)
+    batches, pls = [], []
+    for b in range(3):
+        llr = np.empty((numTb, g), np.float32)
+        pl = rng.integers(0, 2, (numTb, A)).astype(np.int8)
+        for t in range(numTb):
+            orm, _ = O.tx_chain(pl[t], bg, g, qm)
+            llr[t] = nr_link.qam_awgn_llr(orm, qm, 7.6 if t % 2 else 9.0, rng)
+        batches.append(llr)
+        pls.append(pl)
+    dec = LdpcDecoder(bg, mod, 1, 0, precision='fp32')
+    ref = [dec.decodeLLRs(x, A, 8) for x in batches]
+    ref = [(a.copy(), b.copy(), c.copy()) for a, b, c in ref]
+    for t in range(2):   # oracle on a sample of the first batch
+        rr, _, p = O.rate_recover(batches[0][t], A, bg, qm, dtype=np.float32)
+        hard = (OC.decode_beliefs(rr, bg, p["Zc"], p["iLS"], 8, np.float32)[:, :p["K"]] < 0).astype(np.int8)
+        otb, ocb = O.check_crc_and_merge(hard, p["K"], p["F"], p["C"])
+        assert np.array_equal(ref[0][0][t], otb[:A]) and list(ref[0][1][t]) == list(ocb)
+    pend = [dec.decodeLLRsAsync(batches[i], A, 8, slot=i % 2) for i in range(2)]
+    got = [pend[0].result()]
+    got[0] = tuple(x.copy() for x in got[0])
+    pend.append(dec.decodeLLRsAsync(batches[2], A, 8, slot=0))
+    got += [tuple(x.copy() for x in p.result()) for p in pend[1:]]
+    for r, o in zip(ref, got):
+        assert all(np.array_equal(a, b) for a, b in zip(r, o))
+    with pytest.raises(ValueError):
+        dec.decodeLLRsAsync(batches[0][0], A, 8)
+    # two device-resident codecs on two streams
+    codecs = [TbBatchCodec(bg, mod, A, g, precision='fp32', ownHandle=True) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    dl = [torch.from_numpy(x).cuda() for x in batches]
+    torch.cuda.synchronize()
+    outs = []
+    for rep in range(3):
+        for i in range(3):
+            with torch.cuda.stream(streams[i % 2]):
+                o = codecs[i % 2].decode(dl[i], 8)
+            if rep == 2:
+                outs.append(o)
+    torch.cuda.synchronize()
+    for r, o in zip(ref, outs):
+        assert np.array_equal(r[0], o["tb"][:, :A].cpu().numpy()) and np.array_equal(r[1], o["cbOk"].cpu().numpy().astype(bool))
+        assert np.array_equal(r[2], o["tbOk"].cpu().numpy().astype(bool))
