@@ -9,6 +9,9 @@
 #ifndef NR_DEC_PRED_PATH
 #define NR_DEC_PRED_PATH 1   // fp32: predicated FMA-pipe selects in the row body (see sub_sel / twomin_update)
 #endif
+#ifndef NR_DEC_LOADS_FIRST
+#define NR_DEC_LOADS_FIRST 1
+#endif
 #ifndef NR_DEC_LIFT_REGS
 #define NR_DEC_LIFT_REGS 1
 #endif
@@ -332,18 +335,34 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
         // fp32 state: m1s = alpha*min1 (unsigned), m2s = the SIGNED message of the argmin edge (alpha*min2 * sign),
         // sw / rext as below.  Same arithmetic as the generic body, value for value.
         float t[D];
+        const uint32_t rbS = (uint32_t)__cvta_generic_to_shared(rb);
         const float m1o = st.m1s, x2 = st.m2s;
         const uint32_t sw = st.sw;
         const uint32_t oldOff = EXT ? (sw >> OFF_SHIFT) : __float_as_uint(st.rext);
         float min1 = 0.f, min2 = __int_as_float(0x7f800000);
         uint32_t nsw = 0;
+#if NR_DEC_LOADS_FIRST
+        // all gathers of the row first: t[] is live through both phases anyway, so the loads cost no extra registers and
+        // their shared-memory latency overlaps instead of sitting in front of every subtraction
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            if (EXT && j == D - 1)
+                t[j] = st.rext;
+            else
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t[j]) : "r"(rbS + off[j]));
+        }
+#endif
 #pragma unroll
         for (int j = 0; j < D; j++) {
             float rv;
+#if NR_DEC_LOADS_FIRST
+            rv = t[j];
+#else
             if (EXT && j == D - 1)
                 rv = st.rext;
             else
                 rv = *reinterpret_cast<const float*>(rb + off[j]);
+#endif
             const float x1 = FP<float>::flipbits(m1o, sw << (31 - (D - 1 - j)));
             t[j] = sub_sel(rv, x1, x2, off[j], oldOff);
             nsw = __funnelshift_l(__float_as_uint(t[j]), nsw, 1);

@@ -16,6 +16,8 @@ ap.add_argument("--rate", type=float, default=0.6)
 ap.add_argument("--iters", type=int, default=8)
 ap.add_argument("--snrs", default="7.0,7.4,7.8,8.0,8.2,8.4,8.6,8.8,9.0,9.4")
 ap.add_argument("--early-stop", action="store_true")
+ap.add_argument("--batch-tbs", type=int, default=256)
+ap.add_argument("--out", default="")
 args = ap.parse_args()
 rank, world, local = nd.env_rank_world()
 torch.cuda.set_device(local)
@@ -25,7 +27,7 @@ qm = {'QPSK': 2, '16QAM': 4, '64QAM': 6, '256QAM': 8}[args.mod]
 g = int(-(-args.A / args.rate // qm) * qm)
 codec = TbBatchCodec(args.bg, args.mod, args.A, g, precision='fp32', earlyStop=args.early_stop)
 from neoradium_b200.sweep import BlerSweep
-sweep = BlerSweep(codec, numIter=args.iters, tbsPerPoint=args.tbs, batchTbs=256, seed=1)
+sweep = BlerSweep(codec, numIter=args.iters, tbsPerPoint=args.tbs, batchTbs=args.batch_tbs, seed=1)
 clock = [time.perf_counter()]
 
 
@@ -42,6 +44,11 @@ def report(d):
 
 res = sweep.run([float(x) for x in args.snrs.split(",")], on_point=report)
 if rank == 0:
-    print(json.dumps({"config": vars(args), "world": world, "C": codec.C, "Zc": codec.Zc, "points": res}))
+    line = json.dumps({"config": vars(args), "world": world, "C": codec.C, "Zc": codec.Zc, "K": codec.K, "F": codec.F,
+                       "E": codec.lens[0], "points": res})
+    print(line)
+    if args.out:
+        with open(args.out, "a") as f:
+            f.write(line + "\n")
 if world > 1:
     dist.destroy_process_group()
