@@ -10,8 +10,10 @@ A=134760 bits (C=16, K=8448, F=0, E=14040 per block), rv 0, AWGN at Es/N0 = 9.0 
 fp32 (north_star's compute type), no early termination.  A "step" = the fused RX chain (rate recovery -> decode ->
 CRC24B per block -> merge -> CRC24A per transport block) over one such batch.
 
-  value   whole-job decoded information Gbit/s with the LLRs already resident in HBM (A bits per transport block)
-  e2e     the same through the host-buffer API (LdpcDecoder.decodeLLRs on pinned host LLRs, results back on the host)
+  value   whole-job decoded information Gbit/s with the LLRs already resident in HBM (A bits per transport block), two
+          batches in flight on two streams; `single_stream` = the same steps back to back on one stream
+  e2e     the same through the host-buffer API (LdpcDecoder.decodeLLRsAsync on pinned host LLRs, two calls in flight,
+          every step's inputs copied H2D and results read back D2H inside the timed region)
   roofline / cpu_baseline  see DESIGN.md "Measurement"
 The reference arm (--impl reference) times the CPU restatement of the reference's NumPy algorithm (oracle/, pinned
 bit-exact against the unmodified reference) on all host cores; the reference itself is pure Python under
@@ -364,7 +366,7 @@ def run_ours(args):
     lane_rate = 148 * 128 * sm_mhz * 1e6                       # issue slots x 32 lanes per second at the sampled clock
     edge_rate = ncb * EDGE_UPDATES_PER_CB / (kern_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 58.29e6 * ncb / 1024.0, "traffic_source": "profiles/r01_decode_ncu_metrics.csv (ncu --set full, r1c): dram read 57.6 MB + write 0.7 MB per 1024-block launch",
+                "traffic": 58.07e6 * ncb / 1024.0, "traffic_source": "profiles/r01_decode_ncu_metrics.csv (ncu --set full, r1h): dram read 57.64 MB + write 0.43 MB per 1024-block launch",
                 "kernel": "nr_decode_kernel<float, ONE_CB>", "kernel_ms": kern_ms,
                 "kernel_ms_source": "CUDA events around each launch of the single-stream pass (launches do not overlap there)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
