@@ -147,6 +147,16 @@ int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dt
                   int64_t num_cb, int64_t llr_stride, int in_cols, int num_iter, int flags, int out_cols,
                   int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
 
+/* LdpcDecoder.decode2, ldpc.py:1421-1492 (undocumented verification decoder): the same layered schedule -- the reference
+ * walks the P*Zc lifted rows one by one, and the Zc rows of a base-graph row touch disjoint positions -- with the TRUE
+ * second minimum (no "+100000" term), a caller-chosen `alpha`, and an optional stop after the first iteration whose hard
+ * decisions satisfy every parity check.  (The reference's own stop test calls isValidCodedBlock, which looks at the first
+ * base-graph row only, ldpc.py:841-843; here all rows are checked.)  Other arguments as nrldpc_decode; all P rows are
+ * always scheduled. */
+int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr, int64_t num_cb,
+                   int64_t llr_stride, int in_cols, int max_iter, double alpha, int stop_on_good_parity, int out_cols,
+                   int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
+
 /* Fused RX chain: recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A'), i.e. HarqCW.decodeLLRs
  * (harq.py:165-173) / the documented usage ldpc.py:1234-1251, in ONE kernel per code-block group: rate recovery is
  * the decoder's load phase, the CRC runs on the decoder's hard decisions in shared memory.

@@ -116,6 +116,8 @@ SIGNATURES = {
     "nrldpc_rate_recover": (_i32, [_vp, _cfgp, _i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "nrldpc_decode": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
                              _vp]),
+    "nrldpc_decode2": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, ctypes.c_double, _i32, _i32, _vp,
+                              _vp, _vp, _vp]),
     "nrldpc_decode_tb": (_i32, [_vp, _cfgp, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp,
                                 _vp, _vp, _vp]),
     "nrldpc_check_crc_and_merge": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp, _vp]),

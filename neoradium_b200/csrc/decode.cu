@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                     if (ONE_CB || (active && !cbDone)) {
                         RowState<T> st;
                         store.load(row, st);
-                        dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff);
+                        dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff, !a.trueMin2, a.trueMin2 ? (T)a.alpha : (T)0.75);
                         store.store(row, st);
                     }
                     __syncthreads();
@@ -604,7 +604,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + 32 + (size_t)a.cbPerCta * P2) * sizeof(uint32_t) + 16 +
                        (size_t)nT * (sizeof(MinSlot<T>) + sizeof(T));
     // static kernels: mbarriers, CRC factor table, XOR exchange (see the kernel's `extra` region)
-    const bool staticRows = oneCb && sizeof(T) == 4 && !h->noStaticRows;
+    const bool staticRows = oneCb && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2;
     if (staticRows) miscBytes += 16 + 16 + (size_t)2 * nT * sizeof(uint32_t) + 64 * sizeof(uint32_t);
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
@@ -787,6 +787,38 @@ extern "C" int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int
         a.numRows = max(4, min(g.P, rows));
     }
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, s);
+}
+
+extern "C" int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr,
+                              int64_t num_cb, int64_t llr_stride, int in_cols, int max_iter, double alpha,
+                              int stop_on_good_parity, int out_cols, int8_t* bits, void* beliefs, int32_t* iters,
+                              nrldpc_stream stream)
+{
+    if (!h) { nr_set_error("decode2: null handle"); return NRLDPC_ERR_ARG; }
+    NrGraph g;
+    if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
+    if (num_cb <= 0 || in_cols < 0 || in_cols > g.ncols - 2 || out_cols < 1 || out_cols > g.ncols || max_iter < 0 ||
+        llr_stride < (int64_t)in_cols * zc || !(alpha == alpha)) {
+        nr_set_error("decode2: bad arguments");
+        return NRLDPC_ERR_ARG;
+    }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    DecArgs a{};
+    a.numCb = num_cb;
+    a.numIter = max_iter;
+    a.flags = NRLDPC_DEC_ALL_ROWS | (stop_on_good_parity ? NRLDPC_DEC_EARLY_STOP : 0);
+    a.llr = llr;
+    a.llrStride = llr_stride;
+    a.inCols = in_cols;
+    a.outCols = out_cols;
+    a.bits = (signed char*)bits;
+    a.bitsStride = (long long)out_cols * zc;
+    a.beliefs = beliefs;
+    a.iters = iters;
+    a.numRows = g.P;          // every row: the closed form of skipped rows is specific to the standard rule
+    a.trueMin2 = 1;
+    a.alpha = alpha;
+    return dispatch_decode(h, g, a, in_dtype, compute_dtype, (cudaStream_t)stream);
 }
 
 extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,

@@ -61,6 +61,9 @@ struct DecArgs {
     // fused CRC of the static kernels: per-thread factors x^(B (Z-1-m)) mod g for the code-block CRC [0, Z) and the
     // CRC24A partial [Z, 2Z); computed on the host once per configuration and cached in the handle
     const unsigned int* crcFacDev;    // capacity in floats (multiple of 4); 0 = gather straight from global memory
+    // decode2 (ldpc.py:1421-1492): true second minimum and a caller-chosen alpha; generic kernels only
+    int trueMin2;
+    double alpha;
 };
 
 namespace {
@@ -328,10 +331,13 @@ __device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_
 
 template <typename T, int D, bool EXT>
 __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* __restrict__ rb, RowState<T>& st,
-                                               uint32_t slot, uint32_t dummyOff, float onef)
+                                               uint32_t slot, uint32_t dummyOff, float onef, bool stdRule = true,
+                                               T alpha = (T)0.75)
 {
+    // stdRule / alpha: LdpcDecoder.decode (alpha = 0.75 and the "+100000" second-minimum quirk, ldpc.py:1563).  The
+    // decode2 variant (ldpc.py:1421-1492) passes its own alpha and the true second minimum; only the generic kernels do.
     constexpr int OFF_SHIFT = 12;   // EXT rows: D <= 10 sign bits, then the argmin offset
-    if constexpr (sizeof(T) == 4 && NR_DEC_PRED_PATH) {
+    if constexpr (sizeof(T) == 4 && NR_DEC_PRED_PATH) if (stdRule) {
         // fp32 state: m1s = alpha*min1 (unsigned), m2s = the SIGNED message of the argmin edge (alpha*min2 * sign),
         // sw / rext as below.  Same arithmetic as the generic body, value for value.
         float t[D];
@@ -437,11 +443,11 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
     }
     const MinSlot<T> best = slot_read(slot, (T)0);
     // the reference bumps the signed minimum by 1e5 and takes |.| before searching the second minimum (ldpc.py:1563)
-    min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(best.t, (T)100000)));
+    if (stdRule) min2 = FP<T>::mn(min2, FP<T>::abs(FP<T>::add(best.t, (T)100000)));
     const uint32_t par = __popc(nsw) & 1u;
     const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;   // sign of new message j = sign_j * parity
-    m1s = FP<T>::mul(min1, (T)0.75);
-    m2s = FP<T>::mul(min2, (T)0.75);
+    m1s = FP<T>::mul(min1, alpha);
+    m2s = FP<T>::mul(min2, alpha);
     // parity folded into the two candidates by an exact multiplication with +-1 (an XOR here would be re-associated
     // by ptxas into one extra LOP3 per edge)
     const T psign = FP<T>::flip((T)1, par);
@@ -473,35 +479,35 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
 
 template <typename T, int D, bool EXT>
 __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t m,
-                                            Lift ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff)
+                                            Lift ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha)
 {
     uint32_t off[D];
     row_offsets<D, EXT>(g, e0, m, ZB, dummyOff, off);
-    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff, g.onef);
+    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff, g.onef, stdRule, alpha);
 }
 
 template <typename T>
 __device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t m, Lift ZB,
-                                             RowState<T>& st, uint32_t slot, uint32_t dummyOff)
+                                             RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha)
 {
     const int e0 = g.rowEdge0[row];
     const int deg = g.rowEdge0[row + 1] - e0;
     if (row >= 4) {
         switch (deg) {
-            case 3: process_row<T, 3, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 4: process_row<T, 4, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 5: process_row<T, 5, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 6: process_row<T, 6, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 7: process_row<T, 7, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 8: process_row<T, 8, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 9: process_row<T, 9, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            default: process_row<T, 10, true>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 3: process_row<T, 3, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 4: process_row<T, 4, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 5: process_row<T, 5, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 6: process_row<T, 6, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 7: process_row<T, 7, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 8: process_row<T, 8, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 9: process_row<T, 9, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            default: process_row<T, 10, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
         }
     } else {
         switch (deg) {
-            case 8: process_row<T, 8, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            case 10: process_row<T, 10, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
-            default: process_row<T, 19, false>(g, e0, rb, m, ZB, st, slot, dummyOff); break;
+            case 8: process_row<T, 8, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 10: process_row<T, 10, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            default: process_row<T, 19, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
         }
     }
 }

@@ -374,6 +374,37 @@ class LdpcDecoder(LdpcBase):
         return _dev.to_host(bits)
 
     # ------------------------------------------------------------------------------------------------------------------
+    def decode2(self, rxCodeBlock, maxIter=6, onlyInfoBits=True, outputBelief=False, alpha=0.75, stopOnGoodParity=True):
+        """The reference's undocumented verification decoder (ldpc.py:1421-1492): the same layered schedule walked one
+        lifted row at a time, with the true second minimum (no "+100000" term) and a caller-chosen ``alpha``.
+        ``stopOnGoodParity`` stops a block after the first iteration whose hard decisions satisfy EVERY parity check; the
+        reference's own test looks at the first base-graph row only (``isValidCodedBlock``, ldpc.py:841-843), so with
+        ``stopOnGoodParity=True`` it may stop earlier than this one.  ``lastIterations`` holds the per-block counts."""
+        rxCodeBlock = np.asarray(rxCodeBlock)
+        c, nIn = rxCodeBlock.shape
+        z = self.liftingSize
+        P, n, k = params.bg_dims(self.baseGraphNo)
+        assert nIn % z == 0 and nIn // z + 2 == n
+        x = _dev.to_dev(rxCodeBlock if rxCodeBlock.dtype in (np.float32, np.float64) else rxCodeBlock.astype(np.float64))
+        outCols = k if onlyInfoBits else n
+        tdt = _TORCH_F[self.precision]
+        bits = beliefs = None
+        if outputBelief:
+            beliefs = torch.empty((c, outCols * z), dtype=tdt, device=x.device)
+        else:
+            bits = torch.empty((c, outCols * z), dtype=torch.int8, device=x.device)
+        iters = torch.empty((c,), dtype=torch.int32, device=x.device)
+        _native.check(_native.lib().nrldpc_decode2(
+            _dev.handle(), self.baseGraphNo, z, _native.F64 if x.dtype == torch.float64 else _native.F32,
+            _NATIVE_F[self.precision], _dev.ptr(x), c, nIn, nIn // z, int(maxIter), float(alpha),
+            1 if stopOnGoodParity else 0, outCols, _dev.ptr(bits), _dev.ptr(beliefs), _dev.ptr(iters), _dev.stream_ptr()))
+        self.lastIterations = _dev.to_host(iters)
+        out = _dev.to_host(beliefs if outputBelief else bits)
+        if onlyInfoBits:
+            out = out[:, :self.codeBlockSize]
+        return out.astype(np.float64) if outputBelief else out
+
+    # ------------------------------------------------------------------------------------------------------------------
     def checkCrcAndMerge(self, rxCodedBlocks):
         """CRC check of every decoded code block and re-assembly of the transport block (ldpc.py:1584-1619)."""
         rxCodedBlocks = np.asarray(rxCodedBlocks)

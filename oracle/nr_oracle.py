@@ -335,6 +335,76 @@ def decode(rx, bg, zc, ils, num_iter=5, only_info=True, output_belief=False, dty
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# a12  decode2: the row-by-row verification decoder  (ldpc.py:1421-1492)
+# ---------------------------------------------------------------------------------------------------------------------
+def decode2(rx, bg, zc, ils, max_iter=6, only_info=True, output_belief=False, alpha=0.75, stop_on_good_parity=False,
+            stop_rule="all", K=None):
+    """[C, N] LLRs -> bits int8 / float64 beliefs, one lifted parity-check row at a time, exactly as the reference walks
+    them (row = i*Z + m, edges in ascending column order, column index col*Z + (m + V) % Z, ldpc.py:1434-1445):
+        t = rx[cols] - rr;  a = |t|;  j* = first argmin;  min1 = a[j*];  min2 = min_{j != j*} a_j      (:1462-1470)
+        min1 > 0 : rr_j = ((prod(sign t) * sign t_j) * (min2 if j == j* else min1)) * alpha            (:1472-1477)
+        min1 == 0 < min2 : rr_j* = prod(1 - 2 (t < 0)) * min2 * alpha, other rr_j = 0                  (:1478-1481)
+        both zero : rr = 0                                                                           (:1482-1483)
+        rx[cols] = t + rr                                                                            (:1485)
+    `stop_rule`: "all" = stop after an iteration whose hard decisions satisfy every check (what the CUDA path does);
+    "first_row" = what the reference actually tests (isValidCodedBlock returns after the first base-graph row,
+    ldpc.py:841-843).  float64 like the reference."""
+    P, n, k = bg_dims(bg)
+    h = base_graph(bg, zc, ils)
+    rx = np.asarray(rx, np.float64)
+    C = rx.shape[0]
+    rows = []
+    for i in range(P):
+        cols = np.nonzero(h[i] >= 0)[0]
+        for m in range(zc):
+            rows.append(cols * zc + (m + h[i, cols].astype(np.int64)) % zc)
+    out = []
+    for c in range(C):
+        r = np.clip(np.concatenate([np.zeros(2 * zc), rx[c]]), -1e10, 1e10)                      # :1452-1456
+        rr = [np.zeros(len(ix)) for ix in rows]
+        for _ in range(max_iter):
+            for ri, ix in enumerate(rows):
+                t = r[ix] - rr[ri]
+                a = np.abs(t)
+                js = int(np.argmin(a))
+                min1 = a[js]
+                a2 = a.copy()
+                a2[js] = 1e10
+                min2 = a2.min()
+                if min1 > 0:
+                    sg = np.sign(t)
+                    s1 = np.prod(sg) * sg
+                    new = s1 * min1
+                    new[js] = s1[js] * min2
+                    new = new * alpha
+                elif min2 > 0:
+                    new = np.zeros_like(t)
+                    new[js] = np.prod(1 - 2 * (t < 0)) * min2
+                    new = new * alpha
+                else:
+                    new = np.zeros_like(t)
+                rr[ri] = new
+                r[ix] = t + new
+            if stop_on_good_parity:
+                hard = (r < 0).astype(np.int8)
+                if stop_rule == "first_row":
+                    hb = hard.reshape(n, zc)
+                    acc = np.zeros(zc, np.int64)
+                    for j in np.nonzero(h[0] >= 0)[0]:
+                        acc += np.roll(hb[j], -int(h[0, j]))
+                    good = not (acc % 2).any()
+                else:
+                    good = parity_ok(hard, bg, zc, ils)
+                if good:
+                    break
+        out.append(r)
+    out = np.array(out)
+    if only_info:
+        out = out[:, :(k * zc if K is None else K)]
+    return out if output_belief else (out < 0).astype(np.int8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # a11  CRC check + merge  (ldpc.py:1610-1619)
 # ---------------------------------------------------------------------------------------------------------------------
 def check_crc_and_merge(decoded, K, F, C):

@@ -502,3 +502,38 @@ def test_async_host_batches_and_concurrent_codecs():
     for r, o in zip(ref, outs):
         assert np.array_equal(r[0], o["tb"][:, :A].cpu().numpy()) and np.array_equal(r[1], o["cbOk"].cpu().numpy().astype(bool))
         assert np.array_equal(r[2], o["tbOk"].cpu().numpy().astype(bool))
+
+
+def _decode2_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode2_cases.npz"))
+    return g, [str(n) for n in g["names"]]
+
+
+@pytest.mark.parametrize("name", _decode2_cases()[1])
+def test_decode2_vs_reference_outputs_and_oracle(name):
+    """LdpcDecoder.decode2 (ldpc.py:1421-1492) in float64: beliefs equal the unmodified reference's (committed fixture,
+    no stop); with stopOnGoodParity the block stops after the first iteration whose hard decisions satisfy every check,
+    which is what the oracle restatement does with stop_rule='all' (the reference tests the first row only)."""
+    g, _ = _decode2_cases()
+    bg, A, zc, ils, nit, K = (int(v) for v in g[name + "/meta"])
+    alpha = float(g[name + "/alpha"])
+    rr = g[name + "/rr"]
+    dec = LdpcDecoder(bg, 'QPSK', 1, 0)
+    dec.initialize(A + 24)
+    assert (dec.liftingSize, dec.setIndex, dec.codeBlockSize) == (zc, ils, K)
+    bel = dec.decode2(rr, nit, False, True, alpha, False)
+    assert np.array_equal(bel, g[name + "/bel"])
+    assert list(dec.lastIterations) == [nit] * rr.shape[0]
+    assert np.array_equal(dec.decode2(rr, nit, True, False, alpha, False), (g[name + "/bel"][:, :K] < 0).astype(np.int8))
+    bel_s = dec.decode2(rr, nit + 4, False, True, alpha, True)
+    assert np.array_equal(bel_s, O.decode2(rr, bg, zc, ils, nit + 4, False, True, alpha, True, "all"))
+    n_it = int(dec.lastIterations[0])
+    assert np.array_equal(bel_s, O.decode2(rr, bg, zc, ils, n_it, False, True, alpha, False))
+    if n_it < nit + 4:
+        assert O.parity_ok((bel_s[0] < 0).astype(np.int8), bg, zc, ils)
+    # fp32 arithmetic: same hard decisions on these well-conditioned inputs
+    d32 = LdpcDecoder(bg, 'QPSK', 1, 0, precision='fp32')
+    d32.initialize(A + 24)
+    if np.abs(rr).max() > 0 and name != "bg2_z13_zeros":
+        assert np.array_equal(d32.decode2(rr, nit, True, False, alpha, False), (g[name + "/bel"][:, :K] < 0).astype(np.int8))

@@ -150,3 +150,27 @@ def test_gold_sequence_oracle_matches_reference_and_38211_definition():
         assert np.array_equal(np.array(nr_modem.gold_sequence(c_init, n)), ref)
         if n <= 1000:   # the bit-serial definition of TS 38.211 5.2.1 is slow in Python
             assert np.array_equal(np.array(nr_modem.gold_sequence_38211(c_init, n)), ref)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# decode2: oracle restatement pinned by outputs of the unmodified reference
+# (oracle/gen_golden_decode2.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def _decode2_cases():
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode2_cases.npz"))
+    return g, [str(n) for n in g["names"]]
+
+
+@pytest.mark.parametrize("name", _decode2_cases()[1])
+def test_decode2_oracle_matches_reference_outputs(name):
+    g, _ = _decode2_cases()
+    bg, A, zc, ils, nit, K = (int(v) for v in g[name + "/meta"])
+    alpha = float(g[name + "/alpha"])
+    rr = g[name + "/rr"]
+    assert np.array_equal(O.decode2(rr, bg, zc, ils, nit, False, True, alpha, False), g[name + "/bel"])
+    # the reference's stop test only looks at the first base-graph row (ldpc.py:841-843)
+    assert np.array_equal(O.decode2(rr, bg, zc, ils, nit + 4, False, True, alpha, True, "first_row"), g[name + "/bel_stop"])
+    # decode2 without a stop is the layered schedule of decode() with the true second minimum: on inputs where the
+    # "+100000" quirk cannot bite (all |LLR| far below 5e4) and alpha = 0.75 both give the same beliefs
+    if alpha == 0.75 and np.abs(rr).max() < 1e3:
+        assert np.array_equal(g[name + "/bel"], O.decode(rr, bg, zc, ils, nit, False, True))
