@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const uint32_t barStage = barLayer + 8;
     uint32_t* crcFac = reinterpret_cast<uint32_t*>(extra + 16);
     uint32_t* crcRed = crcFac + 2 * nT;
-    float* stage = reinterpret_cast<float*>(crcRed + 64);
+    uint32_t* pk = crcRed + 64;   // bit-packed hard decisions of the early-termination test (a.packWords words)
+    float* stage = reinterpret_cast<float*>(pk + ((SBG != 0) ? a.packWords : 0));
     const bool useStage = (SBG != 0) && a.stageFloats > 0;
     LayerBar lb;
     lb.bar = barLayer;
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             if constexpr (SBG != 0) {
                 RowCtx<T, SBG, 0> c0;
                 prep_row<T, SBG, 0>(g, mU, ZB, store, dummyOff, c0);
-                run_rows_static<T, SBG, 0>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0);
+                run_rows_static<T, SBG, 0>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0,
+                                           (a.flags & NRLDPC_DEC_EARLY_STOP) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr);
             } else {
                 for (int row = 0; row < a.numRows; row++) {
                     if (ONE_CB || (active && !cbDone)) {
@@ -436,6 +438,51 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 }
             }
             if (!cbDone) itersDone = it + 1;
+            if constexpr (SBG != 0) {
+                if (a.flags & NRLDPC_DEC_EARLY_STOP) {
+                    // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed: every warp ballots the sign
+                    // of its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
+                    // neighbouring words); the scheduled extension columns were packed by their rows (run_rows_static); then one thread
+                    // per (row, 32 checks) XORs the shifted words of the row's edges.  ~6 % of an iteration.
+                    const int W = nT >> 5, warp = tid >> 5, lane = tid & 31;
+                    uint32_t* pe = pk + (size_t)ncore * 2 * W;   // extension columns, not doubled
+                    constexpr int NC = (SBG == 1) ? 26 : 14;   // == ncore (k + 4 columns of degree > 1)
+                    {   // all loads first, then ballot + one predicated store per column (lanes 0 and 1 write the two copies)
+                        uint32_t hv[NC];
+                        const uint32_t rAddr = (uint32_t)__cvta_generic_to_shared(rcb + m);
+                        const uint32_t cStride = (uint32_t)Z * (uint32_t)sizeof(T);
+#pragma unroll
+                        for (int col = 0; col < NC; col++)
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv[col]) : "r"(rAddr + (uint32_t)col * cStride + (sizeof(T) == 8 ? 4u : 0u)));
+                        uint32_t pAddr = (uint32_t)__cvta_generic_to_shared(pk + (lane & 1) * W + warp);
+                        const uint32_t pStride = 2u * (uint32_t)W * 4u;
+#pragma unroll
+                        for (int col = 0; col < NC; col++) {
+                            const uint32_t w = __ballot_sync(0xffffffffu, (int)hv[col] < 0);
+                            asm volatile("{.reg .pred p; setp.lt.u32 p, %2, 2; @p st.shared.b32 [%0], %1;}" ::"r"(pAddr), "r"(w), "r"((uint32_t)lane) : "memory");
+                            pAddr += pStride;
+                        }
+                    }
+                    __syncthreads();
+                    uint32_t bad = 0;
+                    for (int task = tid; task < a.numRows * W; task += nT) {
+                        const int row = task / W, w = task - row * W;
+                        const int e0 = g.rowEdge0[row];
+                        const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
+                        uint32_t acc = (row >= 4) ? pe[(row - 4) * W + w] : 0u;
+#pragma unroll 4
+                        for (int e = e0; e < e1; e++) {
+                            const uint32_t raw = g.raw[e];
+                            const uint32_t b = 32u * (uint32_t)w + (raw & 511u);   // first position read by these 32 checks
+                            const uint32_t* pc = pk + (raw >> 9) * 2 * W + (b >> 5);
+                            acc ^= __funnelshift_r(pc[0], pc[1], b & 31u);
+                        }
+                        bad |= acc;
+                    }
+                    const int anyBad = __syncthreads_or(bad != 0);
+                    if (!anyBad) break;
+                }
+            } else
             if (a.flags & NRLDPC_DEC_EARLY_STOP) {
                 // syndrome of the hard decisions after a COMPLETE iteration over the scheduled rows (skipped rows are
                 // satisfied by construction: their parity bit is the parity of the rest)
@@ -605,7 +652,10 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
                        (size_t)nT * (sizeof(MinSlot<T>) + sizeof(T));
     // static kernels: mbarriers, CRC factor table, XOR exchange (see the kernel's `extra` region)
     const bool staticRows = oneCb && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2;
-    if (staticRows) miscBytes += 16 + 16 + (size_t)2 * nT * sizeof(uint32_t) + 64 * sizeof(uint32_t);
+    a.packWords = 0;
+    if (staticRows && (a.flags & NRLDPC_DEC_EARLY_STOP))
+        a.packWords = ((g.ncore * 2 + (a.numRows - 4) + 1) * (nT >> 5) + 3) & ~3;   // +1 row: the funnel shift reads one word past the end
+    if (staticRows) miscBytes += 16 + 16 + (size_t)2 * nT * sizeof(uint32_t) + 64 * sizeof(uint32_t) + (size_t)a.packWords * sizeof(uint32_t);
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
     int occ = h->decOcc > 0 ? h->decOcc : ((oneCb && sizeof(T) == 4) ? 2 : 1);

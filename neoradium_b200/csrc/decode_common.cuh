@@ -64,6 +64,8 @@ struct DecArgs {
     // decode2 (ldpc.py:1421-1492): true second minimum and a caller-chosen alpha; generic kernels only
     int trueMin2;
     double alpha;
+    // static kernels with NRLDPC_DEC_EARLY_STOP: words of the bit-packed hard decisions (multiple of 4), see the kernel
+    int packWords;
 };
 
 namespace {
@@ -76,6 +78,7 @@ struct __align__(16) NrDecGraph {
     float onef;                // 1.0f, opaque to the compiler: an exact register move issued as FMUL on the FMA pipe
     uint16_t rowEdge0[NR_MAX_ROWS + 2];
     uint2 tab[NR_MAX_EDGES];   // x = (shift * S) mod 2^32, y = col*Z*sizeof(T)
+    uint16_t raw[NR_MAX_EDGES];   // (col << 9) | shift: the bit-packed syndrome of the early-termination test
 };
 
 // per-thread "argmin so far" record of a row pass: written with a predicated 64-bit (128-bit for fp64) shared-memory
@@ -589,10 +592,16 @@ __device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift Z
 template <typename T, int BG, int ROW, typename Store>
 __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
-                                                RowCtx<T, BG, ROW>& cur)
+                                                RowCtx<T, BG, ROW>& cur, uint32_t* pe)
 {
     constexpr int D = BgRows<BG>::deg(ROW);
     process_row_at<T, D, (ROW >= 4)>(cur.off, rb, cur.st, slot, dummyOff, g.onef);
+    if constexpr (ROW >= 4) {
+        if (pe) {   // early termination: packed hard decisions of this row's private extension column (see the kernel)
+            const uint32_t w = __ballot_sync(0xffffffffu, FP<T>::sign(cur.st.rext) != 0);
+            if ((threadIdx.x & 31) == 0) pe[(ROW - 4) * (blockDim.x >> 5) + (threadIdx.x >> 5)] = w;
+        }
+    }
     lb.arrive();
     store.store(ROW, cur.st);
     if constexpr (ROW + 1 < BgRows<BG>::P) {
@@ -603,7 +612,7 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
         RowCtx<T, BG, ROW + 1> nxt;
         prep_row<T, BG, ROW + 1>(g, m, ZB, store, dummyOff, nxt);
         lb.wait();
-        run_rows_static<T, BG, ROW + 1>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt);
+        run_rows_static<T, BG, ROW + 1>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
     } else {
         lb.wait();
     }
@@ -752,6 +761,7 @@ void build_dec_graph(const NrGraph& g, NrDecGraph* d)
         const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
         d->tab[e].x = (uint32_t)((uint64_t)sh * d->S);   // mod 2^32
         d->tab[e].y = col * g.Z * (uint32_t)sizeof(T);
+        d->raw[e] = (uint16_t)((col << 9) | sh);
     }
 }
 

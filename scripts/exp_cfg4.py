@@ -11,7 +11,7 @@ dev = torch.device("cuda", 0)
 tbs = int(os.environ.get("TBS", "4096"))
 gen = torch.Generator(device=dev); gen.manual_seed(5)
 res = {}
-for snr in (9.0, 8.6):
+for snr in (10.5, 9.0, 8.6):
     codec0 = TbBatchCodec(1, "16QAM", A, G, precision="fp32", device=dev)
     pl = torch.randint(0, 2, (tbs, A), dtype=torch.int8, device=dev, generator=gen)
     llr = awgn_llr(codec0.encode(pl), 4, snr_db=snr, seed=77, offset=0)

@@ -15,12 +15,12 @@ from neoradium_b200.sweep import BlerSweep
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("bg,mod,qm,A,rate,snr,tbs,batch", [(2, 'QPSK', 2, 500, 0.3, -0.6, 48, 16),
-                                                             (1, '16QAM', 4, 8424 * 2 - 24, 0.6, 8.5, 12, 5)])
-def test_bler_point_counters_equal_oracle(bg, mod, qm, A, rate, snr, tbs, batch):
+@pytest.mark.parametrize("bg,mod,qm,A,rate,snr,tbs,batch,nit", [(2, 'QPSK', 2, 500, 0.3, -0.6, 48, 16, 6),
+                                                                 (1, '16QAM', 4, 8424 * 2 - 24, 0.6, 8.45, 12, 5, 8)])
+def test_bler_point_counters_equal_oracle(bg, mod, qm, A, rate, snr, tbs, batch, nit):
     g = int(-(-A / rate // qm) * qm)
     codec = TbBatchCodec(bg, mod, A, g, precision='fp32')
-    seed, nit = 4242, 6
+    seed = 4242
     d = nd.bler_point(codec, tbs, snr, nit, seed=seed, batch_tbs=batch)
     # the same payloads and noise, regenerated batch by batch exactly as bler_point does, through the oracle
     gen = torch.Generator(device='cuda')
