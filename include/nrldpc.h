@@ -39,8 +39,9 @@ enum {
 /* generator polynomials of chancodebase.py:37-44 */
 enum { NRLDPC_CRC6 = 0, NRLDPC_CRC11 = 1, NRLDPC_CRC16 = 2, NRLDPC_CRC24A = 3, NRLDPC_CRC24B = 4, NRLDPC_CRC24C = 5 };
 
-/* element types of LLR / belief buffers */
-enum { NRLDPC_F32 = 0, NRLDPC_F64 = 1 };
+/* element types of LLR / belief buffers.  NRLDPC_F16 (IEEE half) is an INPUT type of nrldpc_decode_tb only: the values
+ * are widened exactly to the compute type on load, so the result equals that of the same values passed as float. */
+enum { NRLDPC_F32 = 0, NRLDPC_F64 = 1, NRLDPC_F16 = 2 };
 
 /* decoder flags */
 enum {

@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3
 CRC_IDS = {"6": 0, "11": 1, "16": 2, "24A": 3, "24B": 4, "24C": 5}
-F32, F64 = 0, 1
+F32, F64, F16 = 0, 1, 2
 DEC_EARLY_STOP, DEC_ALL_ROWS = 1, 2
 
 

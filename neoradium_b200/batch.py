@@ -14,6 +14,9 @@ import torch
 from . import _dev, _native, params
 
 
+_IN_DTYPE = {torch.float32: _native.F32, torch.float64: _native.F64, torch.float16: _native.F16}
+
+
 class PendingDecode:
     """Result of ``TbBatchCodec.decode_host(..., wait=False)``: ``result()`` returns the host output dict once the last
     D2H copy has landed."""
@@ -87,14 +90,15 @@ class TbBatchCodec:
                     iters=torch.empty((numTb, self.C), dtype=torch.int32, device=dev))
 
     def decode(self, llr, numIter, out=None, softBuffer=None):
-        """llr float32|float64 [numTb, >=G'] (device, row pitch = stride(0)) -> dict(tb, cbOk, tbOk, iters).
+        """llr float32|float64|float16 [numTb, >=G'] (device, row pitch = stride(0)) -> dict(tb, cbOk, tbOk, iters).
+        float16 LLRs are widened exactly to the compute type on load (half the HBM / PCIe bytes of float32).
         One fused kernel pass (+ a tiny per-TB CRC combine) on the current stream; nothing is synchronised."""
         numTb = llr.shape[0]
         if out is None:
             out = self.alloc_outputs(numTb)
         flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
         _native.check(_native.lib().nrldpc_decode_tb(
-            self._h, self.cfg, _native.F64 if llr.dtype == torch.float64 else _native.F32,
+            self._h, self.cfg, _IN_DTYPE[llr.dtype],
             _native.F64 if self.precision == 'fp64' else _native.F32, _dev.ptr(llr), numTb, llr.shape[1],
             llr.stride(0), _dev.ptr(softBuffer), int(numIter), flags, _dev.ptr(out['tb']), self.C * self.per,
             _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']), _dev.ptr(out['iters']), _dev.stream_ptr()))
@@ -102,7 +106,7 @@ class TbBatchCodec:
 
     # ------------------------------------------------------------------------------------------------------------------
     def decode_host(self, llr_host, numIter, out=None, chunks=None, wait=True, slot=0):
-        """Host-buffer entry point: llr_host is a float32|float64 [numTb, G'] HOST array (NumPy array or CPU torch
+        """Host-buffer entry point: llr_host is a float32|float64|float16 [numTb, G'] HOST array (NumPy array or CPU torch
         tensor; pinned memory gives full PCIe speed).  The batch is cut into `chunks` groups of transport blocks and
         pipelined over three CUDA streams -- H2D copy of chunk i+1, fused decode of chunk i and D2H copy of the results of
         chunk i-1 overlap -- and the call returns after everything has landed on the host.
@@ -115,7 +119,7 @@ class TbBatchCodec:
         (``slot`` 0 / 1 select independent device staging buffers; the caller alternates its host buffers likewise) the
         H2D copy of the next batch overlaps the decode and D2H of the current one and PCIe never idles."""
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(llr_host)
-        assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in (torch.float32, torch.float64)
+        assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in _IN_DTYPE
         numTb, Gp = x.shape
         if chunks is None:
             chunks = int(os.environ.get("NRLDPC_HOST_CHUNKS", "4"))

@@ -70,6 +70,23 @@ struct StateStore {
     }
 };
 
+// input element -> compute type (half and float widen exactly)
+template <typename T, typename TIn>
+__device__ __forceinline__ T llr_cvt(TIn v)
+{
+    return (T)v;
+}
+template <>
+__device__ __forceinline__ float llr_cvt<float, __half>(__half v)
+{
+    return __half2float(v);
+}
+template <>
+__device__ __forceinline__ double llr_cvt<double, __half>(__half v)
+{
+    return (double)__half2float(v);
+}
+
 // one input LLR, widened / narrowed to the compute type
 template <typename T>
 __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
@@ -211,10 +228,11 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         long long xBase, xAvail;
         stream_geom(cbi, E, xBase, xAvail);
         const int n = (int)(xAvail < 0 ? 0 : (xAvail > (long long)E ? (long long)E : xAvail));
-        const int head = (int)(xBase & 3);
-        const int nCopy = (head + n) & ~3;
-        stage_issue(barStage, (uint32_t)__cvta_generic_to_shared(stage), reinterpret_cast<const float*>(a.llr) + (xBase - head),
-                    (uint32_t)nCopy * 4u);
+        const int es = a.inF16 ? 2 : 4, epv = 16 / es;   // element size, elements per 16 bytes
+        const int head = (int)(xBase & (epv - 1));
+        const int nCopy = (head + n) & ~(epv - 1);
+        stage_issue(barStage, (uint32_t)__cvta_generic_to_shared(stage),
+                    reinterpret_cast<const char*>(a.llr) + (xBase - head) * es, (uint32_t)(nCopy * es));
     };
     if (useStage && tid == 0 && (long long)blockIdx.x < (a.numCb + cbPerCta - 1) / cbPerCta) stage_block((long long)blockIdx.x);
 
@@ -252,7 +270,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 for (int col = 2; col < colEnd; col++, n += Z) {
                     T v = (T)0;
                     if (!a.rm) {
-                        if (col - 2 < a.inCols) v = (T)x[n];
+                        if (col - 2 < a.inCols) v = llr_cvt<T, TIn>(x[n]);
                     } else if (n < a.ncb) {
                         if (n >= sysLen && n < sysLen + a.F) {
                             v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                                     b = i / Eq;
                                 }
                                 const int xi = (i - b * Eq) * a.qm + b;
-                                const T xv = (xi < xAvailI) ? (T)x[xi] : (T)0;
+                                const T xv = (xi < xAvailI) ? llr_cvt<T, TIn>(x[xi]) : (T)0;
                                 acc = FP<T>::add(acc, xv);
                             }
                             if (sb) sb[q] = acc;
@@ -292,17 +310,19 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                     }
                 }
             };
-            if (useStage && E <= L) {
+            auto staged_load = [&](auto tin) {
+                using TIn = decltype(tin);
+                constexpr int EPV = 16 / (int)sizeof(TIn);   // elements per 16 bytes
                 // staged stream, no repetition (E <= Ncb - F: a buffer position receives at most one LLR): one term per
                 // position, read from shared memory; element xi of the stream sits at stage[head + xi] for head + xi <
-                // nCopy, the (< 4) LLRs behind the last whole 16 bytes come from global memory
-                const float* __restrict__ x = reinterpret_cast<const float*>(a.llr) + xBase;
+                // nCopy, the (< EPV) LLRs behind the last whole 16 bytes come from global memory
+                const TIn* __restrict__ x = reinterpret_cast<const TIn*>(a.llr) + xBase;
                 const int ncb = a.ncb, F = a.F, k0 = a.k0, qm = a.qm;
-                const int head = (int)(xBase & 3);
-                const int nCopy = (head + xAvailI) & ~3;
+                const int head = (int)(xBase & (EPV - 1));
+                const int nCopy = (head + xAvailI) & ~(EPV - 1);
                 mbar_wait(barStage, stagePhase);
                 stagePhase ^= 1u;
-                const float* __restrict__ sp = stage + head;
+                const TIn* __restrict__ sp = reinterpret_cast<const TIn*>(stage) + head;
                 const int nStaged = nCopy - head;
                 int n = m;
                 for (int col = 2; col < lastCol; col++, n += Z) {
@@ -319,8 +339,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                     r += (r < 0) ? Eq : 0;
                     const int xi = r * qm + b;
                     const bool valid = (n < ncb) && !isFill && (i < E) && (xi < xAvailI);
-                    T v = (T)sp[(valid && xi < nStaged) ? xi : 0];
-                    if (valid && xi >= nStaged) v = (T)x[xi];        // the (< 4) LLRs behind the last whole 16 bytes
+                    T v = llr_cvt<T, TIn>(sp[(valid && xi < nStaged) ? xi : 0]);
+                    if (valid && xi >= nStaged) v = llr_cvt<T, TIn>(x[xi]);   // behind the last whole 16 bytes
                     v = FP<T>::mn(v, (T)1e10);                        // np.clip(., -1e10, 1e10), ldpc.py:1536
                     v = FP<T>::mx(v, (T)-1e10);
                     v = FP<T>::add(v, (T)0);                          // -0.0 -> +0.0 (see header)
@@ -333,7 +353,10 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                         store.store(col - ksys, st0);
                     }
                 }
-            } else if (a.rm && !sb && !a.inF64 && smallE) {
+            };
+            if (useStage && E <= L) {
+                if (a.inF16) staged_load(__half()); else staged_load(float());
+            } else if (a.rm && !sb && !a.inF64 && !a.inF16 && smallE) {
                 // common case (fp32 stream, no HARQ history): same arithmetic, none of the generic bookkeeping
                 const float* __restrict__ x = reinterpret_cast<const float*>(a.llr) + xBase;
                 const int ncb = a.ncb, F = a.F, k0 = a.k0, qm = a.qm;
@@ -402,6 +425,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 }
             } else if (a.inF64) {
                 load_cols(double());
+            } else if (a.inF16) {
+                load_cols(__half());
             } else {
                 load_cols(float());
             }
@@ -728,7 +753,8 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     }
     if (staticRows && a.rm && !a.softBuf && !a.inF64 && !h->noStage && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) {
         const int Emax = a.E0 + ((a.nShort < a.C) ? a.fStep : 0);
-        const size_t need = (size_t)((Emax + 3 + 3) & ~3) * sizeof(float);
+        const int es = a.inF16 ? 2 : 4, epv = 16 / es;
+        const size_t need = ((size_t)((Emax + 2 * (epv - 1)) & ~(epv - 1)) * es + 15) & ~(size_t)15;
         const size_t used = rBytes + (size_t)smemRows * rowBytes + miscBytes;
         if (used + need <= budget && need <= (size_t)(1u << 19)) a.stageFloats = (int)(need / sizeof(float));
     }
@@ -773,8 +799,12 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
 
 int dispatch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, int inDtype, int computeDtype, cudaStream_t s)
 {
-    if (inDtype != NRLDPC_F32 && inDtype != NRLDPC_F64) { nr_set_error("decode: bad input dtype"); return NRLDPC_ERR_ARG; }
+    if (inDtype != NRLDPC_F32 && inDtype != NRLDPC_F64 && !(inDtype == NRLDPC_F16 && a.rm)) {
+        nr_set_error("decode: bad input dtype (NRLDPC_F16 is accepted by nrldpc_decode_tb only)");
+        return NRLDPC_ERR_ARG;
+    }
     a.inF64 = (inDtype == NRLDPC_F64);
+    a.inF16 = (inDtype == NRLDPC_F16);
     if (computeDtype == NRLDPC_F32) return launch_decode<float>(h, g, a, s);
     if (computeDtype == NRLDPC_F64) return launch_decode<double>(h, g, a, s);
     nr_set_error("decode: bad compute dtype");
@@ -791,6 +821,10 @@ extern "C" int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int
                              int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream)
 {
     if (!h) { nr_set_error("decode: null handle"); return NRLDPC_ERR_ARG; }
+    if (in_dtype != NRLDPC_F32 && in_dtype != NRLDPC_F64) {
+        nr_set_error("decode: bad input dtype (NRLDPC_F16 is accepted by nrldpc_decode_tb only)");
+        return NRLDPC_ERR_ARG;
+    }
     NrGraph g;
     if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
     if (num_cb <= 0 || in_cols < 0 || in_cols > g.ncols - 2 || out_cols < 1 || out_cols > g.ncols || num_iter < 0 ||

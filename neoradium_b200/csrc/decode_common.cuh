@@ -1,6 +1,7 @@
 // Device/host building blocks of the decoder kernels of decode.cu (arithmetic helpers, row body, split barrier,
 // CRC and TMA staging helpers).
 #pragma once
+#include <cuda_fp16.h>
 #include <string.h>
 
 #include "nr_bg_tables.h"
@@ -38,6 +39,7 @@ struct DecArgs {
     long long llrStride;
     int inCols;
     int inF64;          // element type of `llr` (compute type T is the kernel's template parameter)
+    int inF16;          // llr holds IEEE half values (fused mode only); widened exactly to T on load
     // mode B: fused rate recovery (rm != 0)
     int rm;
     int K, F, C, qm, ncb, k0, E0, nShort, fStep;   // per-TB split: first nShort blocks have E0, the rest E0+fStep

@@ -439,8 +439,9 @@ class LdpcDecoder(LdpcBase):
         """Fused RX chain (extension; the operation sequence of HarqCW.decodeLLRs, harq.py:165-173):
         recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') in one kernel pass.
 
-        ``llrs``: [G] for one transport block or [numTb, G] for a batch of equally configured blocks (float32 or
-        float64; NumPy array or a CUDA torch tensor).  Returns (txBlocks, cbCrc, tbCrc): decoded transport block(s)
+        ``llrs``: [G] for one transport block or [numTb, G] for a batch of equally configured blocks (float32, float64
+        or float16 -- half values are widened exactly on the device and halve the PCIe traffic; NumPy array or a CUDA
+        torch tensor).  Returns (txBlocks, cbCrc, tbCrc): decoded transport block(s)
         WITHOUT the 24 CRC bits ([A] or [numTb, A]), per-code-block CRC results ([C] / [numTb, C]) and the
         transport-block CRC24A result(s).  ``harq`` (single block only) supplies ``rv`` and the soft buffer exactly
         as in ``recoverRate``.  A [numTb, G] HOST batch takes the pipelined path (``TbBatchCodec.decode_host``: chunked
@@ -456,7 +457,7 @@ class LdpcDecoder(LdpcBase):
         onHost = (not isT) or llrs.device.type == 'cpu'
         hdt = llrs.dtype if isT else np.asarray(llrs).dtype
         if (not single) and onHost and harq is None and not returnDevice and \
-                hdt in (torch.float32, torch.float64, np.float32, np.float64):
+                hdt in (torch.float32, torch.float64, torch.float16, np.float32, np.float64, np.float16):
             from .batch import TbBatchCodec
             x = llrs if isT else np.ascontiguousarray(llrs)
             key = (txBlockSize, x.shape[1], precision, self.earlyStop)
@@ -474,7 +475,7 @@ class LdpcDecoder(LdpcBase):
                 return _PendingLLRs(pend, unpack)
             return unpack(codec.decode_host(x, numIter, out=out))
         x = _dev.to_dev(llrs)
-        if x.dtype not in (torch.float32, torch.float64):
+        if x.dtype not in (torch.float32, torch.float64, torch.float16):
             x = x.to(torch.float64)
         x = x.reshape(1, -1) if single else x
         numTb, G = x.shape
@@ -499,8 +500,8 @@ class LdpcDecoder(LdpcBase):
         iters = torch.empty((numTb, c), dtype=torch.int32, device=x.device)
         flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
         _native.check(_native.lib().nrldpc_decode_tb(
-            _dev.handle(), cfg, _native.F64 if x.dtype == torch.float64 else _native.F32, _NATIVE_F[precision],
-            _dev.ptr(x), numTb, G, x.stride(0), _dev.ptr(buf), int(numIter), flags, _dev.ptr(tb), c * per,
+            _dev.handle(), cfg, {torch.float64: _native.F64, torch.float16: _native.F16}.get(x.dtype, _native.F32),
+            _NATIVE_F[precision], _dev.ptr(x), numTb, G, x.stride(0), _dev.ptr(buf), int(numIter), flags, _dev.ptr(tb), c * per,
             _dev.ptr(cbOk), _dev.ptr(tbOk), _dev.ptr(iters), _dev.stream_ptr()))
         if harq is not None:
             newBuf = _dev.to_host(buf).astype(np.float64)

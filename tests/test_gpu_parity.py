@@ -574,3 +574,43 @@ def test_every_lifting_size(bg):
                                               _dev.ptr(bel), None, s))
                 obel = OC.decode_beliefs(llr.astype(odt), bg, zc, ils, 3, odt)
                 assert np.array_equal(bel.cpu().numpy(), obel), (bg, zc, cdt)
+
+
+def test_float16_llr_input_is_exact():
+    """NRLDPC_F16 input (extension): half LLRs are widened exactly on load, so every output equals the one obtained
+    from the same values passed as float32 -- staged (TMA) path at Zc=384, generic path at small Zc, soft-buffer path,
+    host-batch path -- and therefore the oracle's."""
+    rng = np.random.default_rng(16)
+    for bg, A, mod, qm, g, numTb in ((1, 8424 * 3 - 24, '16QAM', 4, 14040 * 3, 5), (2, 500, 'QPSK', 2, 1668, 21),
+                                     (1, 8424 * 2 - 24 - 7, '64QAM', 6, 14040 * 2 - 6, 3)):
+        llr = np.empty((numTb, g), np.float32)
+        for t in range(numTb):
+            orm, _ = O.tx_chain(rng.integers(0, 2, A).astype(np.int8), bg, g, qm)
+            llr[t] = nr_link.qam_awgn_llr(orm, qm, 3.0 + 10 * np.log10(A / g * qm) + (2.5 if qm > 2 else 0), rng)
+        h16 = llr.astype(np.float16)
+        as32 = h16.astype(np.float32)
+        codec = TbBatchCodec(bg, mod, A, g, precision='fp32')
+        o32 = codec.decode(torch.from_numpy(as32).cuda(), 6)
+        o16 = codec.decode(torch.from_numpy(h16).cuda(), 6)
+        for k in ('tb', 'cbOk', 'tbOk', 'iters'):
+            assert torch.equal(o32[k], o16[k]), (bg, k)
+        rr, _, p = O.rate_recover(as32[0], A, bg, qm, dtype=np.float32)
+        hard = (OC.decode_beliefs(rr, bg, p["Zc"], p["iLS"], 6, np.float32)[:, :p["K"]] < 0).astype(np.int8)
+        otb, _ = O.check_crc_and_merge(hard, p["K"], p["F"], p["C"])
+        assert np.array_equal(o16['tb'][0].cpu().numpy(), otb)
+        # soft-buffer (HARQ) path
+        sb32 = torch.zeros((numTb * codec.C, codec.ncb - codec.F), dtype=torch.float32, device='cuda')
+        sb16 = torch.zeros_like(sb32)
+        a = codec.decode(torch.from_numpy(as32).cuda(), 4, softBuffer=sb32)
+        b = codec.decode(torch.from_numpy(h16).cuda(), 4, softBuffer=sb16)
+        assert torch.equal(sb32, sb16) and torch.equal(a['tb'], b['tb'])
+        # host batch through the drop-in class
+        dec = LdpcDecoder(bg, mod, 1, 0, precision='fp32')
+        r32 = dec.decodeLLRs(as32, A, 6)
+        r16 = dec.decodeLLRs(h16, A, 6)
+        assert all(np.array_equal(x, y) for x, y in zip(r32, r16))
+        one = dec.decodeLLRs(h16[0], A, 6)
+        assert np.array_equal(one[0], r16[0][0])
+    with pytest.raises(ValueError):   # decode() of rate-recovered blocks takes float32 / float64
+        _native.check(_native.lib().nrldpc_decode(_dev.handle(), 1, 384, _native.F16, _native.F32, None, 1, 66 * 384, 66, 1, 0, 22,
+                                                  None, None, None, _dev.stream_ptr()))
