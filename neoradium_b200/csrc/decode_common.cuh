@@ -10,6 +10,9 @@
 #ifndef NR_DEC_PRED_PATH
 #define NR_DEC_PRED_PATH 1   // fp32: predicated FMA-pipe selects in the row body (see sub_sel / twomin_update)
 #endif
+#ifndef NR_DEC_PREGATHER
+#define NR_DEC_PREGATHER 1   // gather next-row posteriors of columns the current row does not write ahead of the barrier
+#endif
 #ifndef NR_DEC_LOADS_FIRST
 #define NR_DEC_LOADS_FIRST 1
 #endif
@@ -334,11 +337,13 @@ __device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_
     for (int j = 0; j < D; j++) off[j] = (EXT && j == D - 1) ? dummyOff : lifted_offset(m, ZB, g.tab[e0 + j]);
 }
 
-template <typename T, int D, bool EXT>
+template <typename T, int D, bool EXT, uint32_t PRE = 0>
 __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* __restrict__ rb, RowState<T>& st,
                                                uint32_t slot, uint32_t dummyOff, float onef, bool stdRule = true,
-                                               T alpha = (T)0.75)
+                                               T alpha = (T)0.75, const float* pre = nullptr)
 {
+    // PRE (static fp32 schedule): bit j set = the posterior of edge j was gathered ahead of the layer barrier into pre[j]
+    // (its column is not touched by the previous row, see run_rows_static)
     // stdRule / alpha: LdpcDecoder.decode (alpha = 0.75 and the "+100000" second-minimum quirk, ldpc.py:1563).  The
     // decode2 variant (ldpc.py:1421-1492) passes its own alpha and the true second minimum; only the generic kernels do.
     constexpr int OFF_SHIFT = 12;   // EXT rows: D <= 10 sign bits, then the argmin offset
@@ -359,6 +364,8 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
         for (int j = 0; j < D; j++) {
             if (EXT && j == D - 1)
                 t[j] = st.rext;
+            else if ((PRE >> j) & 1u)
+                t[j] = pre[j];
             else
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t[j]) : "r"(rbS + off[j]));
         }
@@ -581,7 +588,31 @@ struct RowCtx {   // what a thread prepares for a row before it may touch the po
     static constexpr int D = BgRows<BG>::deg(ROW);
     uint32_t off[D];
     RowState<T> st;
+    float pre[D];   // posteriors gathered ahead of the barrier (edges of pregather_mask)
 };
+
+// Edges of row ROW whose column is NOT an edge of row ROW - 1: the previous layer does not write them, and every older
+// write is already ordered by an earlier barrier, so they may be gathered BEFORE the barrier that ends row ROW - 1.
+// Row 0 follows the last scheduled row of the previous iteration (a run-time quantity): nothing is pre-gathered there.
+template <int BG, int ROW>
+__host__ __device__ constexpr uint32_t pregather_mask()
+{
+#if NR_DEC_PREGATHER
+    if (ROW == 0) return 0u;
+    const int e0 = BgRows<BG>::e0(ROW), d = BgRows<BG>::deg(ROW) - (ROW >= 4 ? 1 : 0);
+    const int p0 = BgRows<BG>::e0(ROW > 0 ? ROW - 1 : 0), pd = BgRows<BG>::deg(ROW > 0 ? ROW - 1 : 0);
+    uint32_t mask = 0;
+    for (int j = 0; j < d; j++) {
+        const int col = BG == 1 ? NR_BG1_COL[e0 + j] : NR_BG2_COL[e0 + j];
+        bool hit = false;
+        for (int k = 0; k < pd; k++) hit = hit || ((BG == 1 ? NR_BG1_COL[p0 + k] : NR_BG2_COL[p0 + k]) == col);
+        if (!hit) mask |= 1u << j;
+    }
+    return mask;
+#else
+    return 0u;
+#endif
+}
 
 template <typename T, int BG, int ROW, typename Store>
 __device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift ZB, const Store& store,
@@ -591,13 +622,23 @@ __device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift Z
     row_offsets<BgRows<BG>::deg(ROW), (ROW >= 4)>(g, BgRows<BG>::e0(ROW), m, ZB, dummyOff, c.off);
 }
 
+template <typename T, int BG, int ROW>
+__device__ __forceinline__ void pregather_row(const char* rb, RowCtx<T, BG, ROW>& c)
+{
+    constexpr uint32_t PRE = pregather_mask<BG, ROW>();
+    const uint32_t rbS = (uint32_t)__cvta_generic_to_shared(rb);
+#pragma unroll
+    for (int j = 0; j < BgRows<BG>::deg(ROW); j++)
+        if ((PRE >> j) & 1u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.pre[j]) : "r"(rbS + c.off[j]));
+}
+
 template <typename T, int BG, int ROW, typename Store>
 __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
                                                 RowCtx<T, BG, ROW>& cur, uint32_t* pe)
 {
     constexpr int D = BgRows<BG>::deg(ROW);
-    process_row_at<T, D, (ROW >= 4)>(cur.off, rb, cur.st, slot, dummyOff, g.onef);
+    process_row_at<T, D, (ROW >= 4), pregather_mask<BG, ROW>()>(cur.off, rb, cur.st, slot, dummyOff, g.onef, true, (T)0.75, cur.pre);
     if constexpr (ROW >= 4) {
         if (pe) {   // early termination: packed hard decisions of this row's private extension column (see the kernel)
             const uint32_t w = __ballot_sync(0xffffffffu, FP<T>::sign(cur.st.rext) != 0);
@@ -613,6 +654,7 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
         }
         RowCtx<T, BG, ROW + 1> nxt;
         prep_row<T, BG, ROW + 1>(g, m, ZB, store, dummyOff, nxt);
+        if constexpr (sizeof(T) == 4) pregather_row<T, BG, ROW + 1>(rb, nxt);
         lb.wait();
         run_rows_static<T, BG, ROW + 1>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
     } else {
