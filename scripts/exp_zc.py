@@ -1,0 +1,27 @@
+"""Decoder throughput per lifting size (edge-updates/s), mode A (rate-recovered LLRs, all N columns sent), fp32, 8 iterations."""
+import os, sys, json
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from neoradium_b200 import _native, _dev
+L, h = _native.lib(), _dev.handle()
+res = {}
+for bg, n, k, edges in ((1, 68, 22, 316), (2, 52, 10, 197)):
+    for zc in (384, 352, 320, 256, 240, 208, 192, 176, 128, 96, 64, 32, 16, 8):
+        numCb = max(2048, min(65536, (1 << 24) // (n * zc)))
+        x = torch.randn((numCb, (n - 2) * zc), device='cuda') * 2 + 1.5
+        bits = torch.empty((numCb, k * zc), dtype=torch.int8, device='cuda')
+        s = _dev.stream_ptr()
+        def run():
+            _native.check(L.nrldpc_decode(h, bg, zc, _native.F32, _native.F32, _dev.ptr(x), numCb, (n - 2) * zc, n - 2, 8, 2, k,
+                                          _dev.ptr(bits), None, None, s))
+        run(); run(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        geups = numCb * edges * zc * 8 / ms / 1e6
+        print("BG%d Zc=%3d  %6d blocks  %8.3f ms  %7.1f G edge-updates/s  %6.2f Mcb/s" % (bg, zc, numCb, ms, geups, numCb / ms / 1e3), flush=True)
+        res["bg%d_z%d" % (bg, zc)] = dict(blocks=numCb, ms=ms, g_edge_updates_per_s=geups)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "exp_zc.json"), "w"), indent=1)
