@@ -164,12 +164,11 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const uint32_t dummyOff = (uint32_t)(reinterpret_cast<char*>(dummyW) - rb);
     const int ksys = g.ksys;
 
-    // static kernels: [2 mbarriers | CRC factor table 2 x nT | XOR exchange 2 x 32 | LLR staging buffer]
+    // static kernels: [2 mbarriers | XOR exchange 2 x 32 | packed hard decisions (early stop) | LLR staging buffer]
     unsigned char* extra = smemRaw + ((slotOfs + (size_t)nT * (sizeof(MinSlot<T>) + sizeof(T)) + 15) & ~(size_t)15);
     const uint32_t barLayer = (uint32_t)__cvta_generic_to_shared(extra);
     const uint32_t barStage = barLayer + 8;
-    uint32_t* crcFac = reinterpret_cast<uint32_t*>(extra + 16);
-    uint32_t* crcRed = crcFac + 2 * nT;
+    uint32_t* crcRed = reinterpret_cast<uint32_t*>(extra + 16);
     uint32_t* pk = crcRed + 64;   // bit-packed hard decisions of the early-termination test (a.packWords words)
     float* stage = reinterpret_cast<float*>(pk + ((SBG != 0) ? a.packWords : 0));
     const bool useStage = (SBG != 0) && a.stageFloats > 0;
@@ -203,10 +202,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const NrCrcPoly polyCb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
     const NrCrcPoly polyA = nr_crc_poly(NRLDPC_CRC24A);
     if (wantCrc) {
-        if (SBG != 0) {
-            crcFac[tid] = a.crcFacDev[tid];
-            crcFac[nT + tid] = a.crcFacDev[nT + tid];
-        } else {
+        if (SBG == 0) {
             crc_factors(fac, Lk, Z, P2, polyCb.poly, polyCb.len, tid);
             if (a.C > 1) crc_factors(fac + 16, per, Z, P2, polyA.poly, polyA.len, tid);
         }
@@ -580,8 +576,28 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             // checkCrcAndMerge (ldpc.py:1610-1619) on the hard decisions still in shared memory
             uint32_t remCb, remA;
             if constexpr (SBG != 0) {
-                uint32_t pc = crc_chunk_product<T>(rcb, Lk, Z, m, crcFac[tid], polyCb.poly, polyCb.len);
-                uint32_t pa = (a.C > 1) ? crc_chunk_product<T>(rcb, per, Z, m, crcFac[nT + tid], polyA.poly, polyA.len) : 0u;
+                // CRC by linearity: remainder = XOR over the set bits i of x^(len-1-i) mod g.  Thread m owns bit col*Z + m of
+                // every systematic column; the per-bit constants come from a per-configuration table in global memory
+                // ([2][ksys][Z] words, L2-resident, coalesced; 0 beyond the message, so fillers and the CRC24A/B length
+                // difference need no branches).  ~6 instructions per bit for both CRCs instead of a bit-serial division.
+                constexpr int KS = (SBG == 1) ? 22 : 10;
+                uint32_t pc = 0, pa = 0;
+                {
+                    const unsigned int* __restrict__ tc = a.crcFacDev + m;
+                    const bool two = a.C > 1;
+                    uint32_t cc[KS], ca[KS];
+#pragma unroll
+                    for (int col = 0; col < KS; col++) {
+                        cc[col] = tc[col * Z];
+                        ca[col] = two ? tc[(KS + col) * Z] : 0u;
+                    }
+#pragma unroll
+                    for (int col = 0; col < KS; col++) {
+                        const uint32_t sm = (uint32_t)((int)FP<T>::hibits(rcb[col * Z + m]) >> 31);   // all ones when the bit is 1
+                        pc ^= sm & cc[col];
+                        pa ^= sm & ca[col];
+                    }
+                }
                 pc = __reduce_xor_sync(0xffffffffu, pc);
                 pa = __reduce_xor_sync(0xffffffffu, pa);
                 if ((tid & 31) == 0) {
@@ -680,7 +696,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     a.packWords = 0;
     if (staticRows && (a.flags & NRLDPC_DEC_EARLY_STOP))
         a.packWords = ((g.ncore * 2 + (a.numRows - 4) + 1) * (nT >> 5) + 3) & ~3;   // +1 row: the funnel shift reads one word past the end
-    if (staticRows) miscBytes += 16 + 16 + (size_t)2 * nT * sizeof(uint32_t) + 64 * sizeof(uint32_t) + (size_t)a.packWords * sizeof(uint32_t);
+    if (staticRows) miscBytes += 16 + 16 + 64 * sizeof(uint32_t) + (size_t)a.packWords * sizeof(uint32_t);
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
     int occ = h->decOcc > 0 ? h->decOcc : ((oneCb && sizeof(T) == 4) ? 2 : 1);
@@ -727,26 +743,29 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     a.stageFloats = 0;
     a.crcFacDev = nullptr;
     if (staticRows && a.rm && (a.tbBits || a.cbCrcOk || a.cbRemA)) {
-        // per-thread CRC factors (see crc_chunk_product): f_m = x^(B (Z-1-m)) mod g, B = ceil(len / Z)
+        // per-bit CRC constants x^(len-1-i) mod g, i = col*Z + m, laid out [which][col][Z]; which = 0: the code-block CRC over
+        // the K-F bits, 1: the CRC24A partial over the payload part (C > 1).  0 beyond the message.
         const int Lk = a.K - a.F, per = (a.C > 1) ? Lk - 24 : Lk;
-        const unsigned long long key = ((unsigned long long)(unsigned)Lk << 32) | ((unsigned)Z << 12) | (unsigned)(a.C > 1);
+        const unsigned long long key = ((unsigned long long)(unsigned)Lk << 32) | ((unsigned)Z << 12) | ((unsigned)g.ksys << 1) | (unsigned)(a.C > 1);
+        const size_t words = (size_t)2 * g.ksys * Z;
         if (!h->crcFacDev || h->crcFacKey != key) {
-            if (!h->crcFacDev) NR_CUDA_CHECK(cudaMalloc(&h->crcFacDev, 2 * NR_MAX_Z * sizeof(unsigned int)));
-            unsigned int host[2 * NR_MAX_Z];
+            if (!h->crcFacDev) NR_CUDA_CHECK(cudaMalloc(&h->crcFacDev, (size_t)2 * 22 * NR_MAX_Z * sizeof(unsigned int)));
+            unsigned int* host = (unsigned int*)calloc(words, sizeof(unsigned int));
+            if (!host) { nr_set_error("decode: out of host memory"); return NRLDPC_ERR_NOMEM; }
             const NrCrcPoly pc = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A), pa = nr_crc_poly(NRLDPC_CRC24A);
             for (int which = 0; which < 2; which++) {
                 const NrCrcPoly pp = which ? pa : pc;
                 const int len = which ? per : Lk;
-                const uint32_t base = nr_gf_xpow((len + Z - 1) / Z, pp.poly, pp.len);
-                uint32_t f = 1;
-                for (int m = Z - 1; m >= 0; m--) {
-                    host[which * Z + m] = f;
-                    f = nr_gf_mulmod(f, base, pp.poly, pp.len);
+                uint32_t f = 1;   // x^0 for the last bit
+                for (int i = len - 1; i >= 0; i--) {
+                    host[(size_t)which * g.ksys * Z + i] = f;   // i = col*Z + m is exactly the [col][Z] layout
+                    f = nr_gf_mulmod(f, 2u, pp.poly, pp.len);
                 }
             }
-            // the kernel reads [0, nT) and [nT, 2 nT) with nT == Z for the static kernels
-            NR_CUDA_CHECK(cudaMemcpyAsync(h->crcFacDev, host, 2 * Z * sizeof(unsigned int), cudaMemcpyHostToDevice, s));
-            NR_CUDA_CHECK(cudaStreamSynchronize(s));   // `host` is a stack buffer
+            cudaError_t ce = cudaMemcpyAsync(h->crcFacDev, host, words * sizeof(unsigned int), cudaMemcpyHostToDevice, s);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);   // `host` is freed below
+            free(host);
+            NR_CUDA_CHECK(ce);
             h->crcFacKey = key;
         }
         a.crcFacDev = (const unsigned int*)h->crcFacDev;
