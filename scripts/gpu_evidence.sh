@@ -1,0 +1,16 @@
+#!/bin/bash
+# One GPU box, everything the numbers in profiles/ and DESIGN.md come from (run as: gpurun -- 'bash scripts/gpu_evidence.sh').
+mkdir -p gpurun_out
+timeout 1000 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python -c "import __graft_entry__ as g; g.smoke()"
+# launch list (per-launch device times are cold-cache and serialised: use the shares) and one full capture of the decoder
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 4 --warmup 3 --no-cpu > gpurun_out/ncu_l.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:nr_decode -s 4 -c 1 -o gpurun_out/decode -f python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_f.log 2>&1
+# the bench lines (never taken under the profiler)
+timeout 400 python bench.py --steps 50 --warmup 5 > gpurun_out/bench.json 2>gpurun_out/bench.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>/dev/null
+# helper kernels, config 4 (early termination), per-lifting-size throughput
+for NTB in 256 1024; do NTB=$NTB timeout 300 python scripts/bench_kernels.py > gpurun_out/helpers_$NTB.json 2>/dev/null; done
+timeout 600 python scripts/exp_cfg4.py 2>&1 | tail -7
+timeout 600 python scripts/exp_zc.py > gpurun_out/exp_zc.log 2>&1
+tail -c 600 gpurun_out/bench.json
