@@ -550,7 +550,7 @@ struct BgRows {
 //   mode 0: plain bar.sync at the wait point   mode 1: mbarrier, one arrival per warp   mode 2: hardware cluster
 //   barrier of the (implicit 1-CTA) cluster, which is split-phase by construction
 #ifndef NR_DEC_BAR_MODE
-#define NR_DEC_BAR_MODE 0   // measured on B200 (BG1 Zc=384, 1024 blocks): mode 0 563 us, mode 1 567 us, mode 2 635 us
+#define NR_DEC_BAR_MODE 1   // measured on B200 (BG1 Zc=384, 1024 blocks, r1j): mode 1 +0.5-0.8 % over mode 0 now that gathers sit between arrive and wait; mode 2 slower
 #endif
 struct LayerBar {
     uint32_t bar;     // shared-memory address of the mbarrier (mode 1)
