@@ -72,6 +72,25 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, ok, tb
 
 
+def _cpu_worker_c(args):
+    """The same chain with the compiled scalar C restatement (oracle/nr_oracle_c.c: float64 decode of all 46 rows,
+    bit-serial CRC) -- a secondary, friendlier CPU figure than the reference's NumPy code."""
+    llr, reps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import nr_oracle as O
+    import nr_oracle_c as OC
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        rr, _, p = O.rate_recover(llr.astype(np.float64), A, BG, QM)
+        bel = OC.decode_beliefs(rr, BG, p["Zc"], p["iLS"], NUM_ITER, np.float64)
+        bits = (bel[:, :p["K"]] < 0).astype(np.int8)
+        cb_ok = [OC.crc(bits[r, :p["K"] - p["F"]], '24B') == 0 for r in range(p["C"])]
+        tb = np.concatenate([bits[r, :p["K"] - p["F"] - 24] for r in range(p["C"])])
+        tb_ok = OC.crc(tb, '24A') == 0
+    return time.perf_counter() - t0, bool(tb_ok) and all(cb_ok), tb[:A]
+
+
 def _cpu_make_llr(seed):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
@@ -83,13 +102,13 @@ def _cpu_make_llr(seed):
     return nr_link.qam_awgn_llr(rm, QM, SNR_DB, rng, np.float32), tb
 
 
-def cpu_baseline(llr_list, cores, reps=1):
+def cpu_baseline(llr_list, cores, reps=1, worker=_cpu_worker):
     """All `cores` workers decode one transport block each (bounded sample); returns (Gbit/s, seconds, outputs)."""
     import multiprocessing as mp
     jobs = [(llr_list[i % len(llr_list)], reps) for i in range(cores)]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
-        res = pool.map(_cpu_worker, jobs)
+        res = pool.map(worker, jobs)
     wall = time.perf_counter() - t0
     bits = cores * reps * A
     return bits / wall / 1e9, wall, res
@@ -411,6 +430,12 @@ def run_ours(args):
                "sample": "%d transport blocks (%d code blocks) of the timed batch, one per host core, NumPy oracle port "
                          "of the reference algorithm in float64, %.1f s wall" % (cores, cores * C_PER_TB, wall),
                "bits_identical_to_gpu": bool(same)}
+        gbps_c, wall_c, res_c = cpu_baseline(sample, cores, reps=4, worker=_cpu_worker_c)
+        cpu["c_port"] = {"value": gbps_c, "unit": UNIT, "cores": cores,
+                         "note": "secondary: the same sample x4 through the compiled scalar C restatement (oracle/nr_oracle_c.c, "
+                                 "gcc -O2, float64, all 46 rows, bit-serial CRC), %.1f s wall" % wall_c,
+                         "bits_identical_to_numpy_port": bool(all(np.array_equal(res_c[i][2], res_cpu[i][2])
+                                                                  for i in range(len(res_c))))}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

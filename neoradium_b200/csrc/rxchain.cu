@@ -55,6 +55,94 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Staged form (the one that normally runs).  The block's slice of the rate-matched stream is read with 16-byte loads and
+// DE-INTERLEAVED ON THE WAY INTO SHARED MEMORY (xs[b * Eq + s] = stream[s * qm + b], ldpc.py:1405; the division by qm is a
+// multiply-high by a host-computed reciprocal), so that shared memory holds the sequence e[i] the circular buffer receives.
+// The circular buffer is then walked in up to three segments (cut at k0 and at the filler gap) inside which both the
+// stream index i = q + c and the output index n = q + d are affine in the buffer position q: the inner loop is one
+// conflict-free LDS, one add and one coalesced store per element, no index arithmetic.  Positions that receive more
+// than one LLR (E > L: repetition) add their further terms in ascending stream order, as the reference's chunked `+=`.
+template <typename T, bool SB>
+__global__ void __launch_bounds__(256)
+    nr_rate_recover_staged_kernel(const T* __restrict__ llr, long long numCb, long long llrLen, long long llrStride, int C,
+                                  int K, int F, int Z, int ncb, int k0, int qm, uint32_t qmMagic, int E0, int nShort,
+                                  int fStep, T* softBuf, T* __restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char rrSmem[];
+    T* xs = reinterpret_cast<T*>(rrSmem);
+    constexpr int EPV = 16 / (int)sizeof(T);
+    const int L = ncb - F;
+    const int sysLen = K - 2 * Z - F;
+    const int nT = blockDim.x, tid = threadIdx.x;
+    const int k0m = k0 % L;
+    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
+        const long long tb = cb / C;
+        const int r = (int)(cb - tb * C);
+        const int E = E0 + (r >= nShort ? fStep : 0);
+        const long long off = (long long)r * E0 + (long long)(r > nShort ? r - nShort : 0) * fStep;
+        const int Eq = E / qm;
+        const T* __restrict__ xg = llr + tb * llrStride + off;
+        const long long availL = llrLen - off;   // missing tail LLRs count as zeros (ldpc.py:1402-1403)
+        const int avail = (int)(availL < 0 ? 0 : (availL > (long long)E ? (long long)E : availL));
+        const int head = (int)((reinterpret_cast<uintptr_t>(xg) / sizeof(T)) & (EPV - 1));
+        __syncthreads();   // the previous block's gathers are done
+        {
+            const int nvec = (head + E + EPV - 1) / EPV;
+            const uint4* __restrict__ src4 = reinterpret_cast<const uint4*>(xg - head);   // 16-byte aligned (host checks `llr`)
+#pragma unroll 2
+            for (int v = tid; v < nvec; v += nT) {
+                const int xi0 = v * EPV - head;
+                T vals[EPV];
+                if (xi0 >= 0 && xi0 + EPV <= avail) {
+                    const uint4 w = __ldg(src4 + v);
+                    memcpy(vals, &w, 16);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < EPV; k++) {
+                        const int xi = xi0 + k;
+                        vals[k] = (xi >= 0 && xi < avail) ? xg[xi] : (T)0;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < EPV; k++) {
+                    const int xi = xi0 + k;
+                    if (xi >= 0 && xi < E) {
+                        const int s = qm == 1 ? xi : (int)__umulhi((uint32_t)xi, qmMagic);
+                        const int b = xi - s * qm;
+                        xs[b * Eq + s] = vals[k];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        T* sb = SB ? softBuf + cb * (long long)L : nullptr;
+        T* __restrict__ o = out + cb * (long long)ncb;
+        for (int f = tid; f < F; f += nT) o[sysLen + f] = (T)1e20;   // LARGE_LLR, chancodebase.py:52
+        auto seg = [&](int qlo, int qhi) {   // buffer positions [qlo, qhi): i = q + c, n = q + d
+            if (qlo >= qhi) return;
+            const int c = (qlo < k0m) ? L - k0m : -k0m;
+            const int d = (qlo < sysLen) ? 0 : F;
+            const int qData = min(qhi, E - c);   // positions that receive at least one LLR
+            const T* __restrict__ xc = xs + c;
+            T* __restrict__ od = o + d;
+            int q = qlo + tid;
+#pragma unroll 4
+            for (; q < qData; q += nT) {
+                T acc = Add<T>::f(SB ? sb[q] : (T)0, xc[q]);
+                for (int i = q + c + L; i < E; i += L) acc = Add<T>::f(acc, xs[i]);
+                if (SB) sb[q] = acc;
+                od[q] = acc;
+            }
+#pragma unroll 4
+            for (; q < qhi; q += nT) od[q] = SB ? sb[q] : (T)0;   // nothing received: the soft buffer (or 0) as it is
+        };
+        const int cutA = min(k0m, sysLen), cutB = max(k0m, sysLen);
+        seg(0, cutA);
+        seg(cutA, cutB);
+        seg(cutB, L);
+    }
+}
+
 }   // namespace
 
 extern "C" int nrldpc_rate_recover(nrldpc_handle* h, const nrldpc_tb_config* cfg, int dtype, const void* llr,
@@ -72,8 +160,40 @@ extern "C" int nrldpc_rate_recover(nrldpc_handle* h, const nrldpc_tb_config* cfg
     nr_tb_split(cfg, N, &E0, &nShort, &fStep, &k0);
     NR_CUDA_CHECK(cudaSetDevice(h->device));
     const long long numCb = num_tb * cfg->C;
-    const int grid = (int)min(numCb, (long long)h->numSMs * 8);
     cudaStream_t s = (cudaStream_t)stream;
+    // staged kernel: needs the block's stream slice in shared memory and a 16-byte aligned `llr`
+    const int Emax = E0 + fStep;
+    const size_t esz = dtype == NRLDPC_F64 ? 8 : 4;
+    const size_t smem = (size_t)Emax * esz;
+    const bool staged = (dtype == NRLDPC_F32 || dtype == NRLDPC_F64) && smem <= (size_t)h->maxSmemOptin &&
+                        ((uintptr_t)llr & 15) == 0 && E0 >= cfg->qm && !getenv("NRLDPC_RR_GENERIC");
+    if (staged) {
+        int perSM = (int)((size_t)h->smemPerSM / (smem + 1024));
+        perSM = perSM < 1 ? 1 : (perSM > 8 ? 8 : perSM);
+        const int grid = (int)min(numCb, (long long)h->numSMs * perSM);
+        const uint32_t magic = cfg->qm > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)cfg->qm - 1) / (uint64_t)cfg->qm) : 0u;
+#define NR_RR_LAUNCH(T, SBF)                                                                                          \
+    do {                                                                                                              \
+        if (smem > 48 * 1024)                                                                                         \
+            NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_recover_staged_kernel<T, SBF>,                                 \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
+        nr_rate_recover_staged_kernel<T, SBF><<<grid, 256, smem, s>>>((const T*)llr, numCb, llr_len, llr_stride, cfg->C, \
+                                                                      cfg->K, cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, \
+                                                                      magic, E0, nShort, fStep, (T*)soft_buffer,      \
+                                                                      (T*)out);                                       \
+    } while (0)
+        if (dtype == NRLDPC_F32) {
+            if (soft_buffer) NR_RR_LAUNCH(float, true);
+            else NR_RR_LAUNCH(float, false);
+        } else {
+            if (soft_buffer) NR_RR_LAUNCH(double, true);
+            else NR_RR_LAUNCH(double, false);
+        }
+#undef NR_RR_LAUNCH
+        NR_CUDA_CHECK(cudaGetLastError());
+        return NRLDPC_OK;
+    }
+    const int grid = (int)min(numCb, (long long)h->numSMs * 8);
     if (dtype == NRLDPC_F32)
         nr_rate_recover_kernel<float><<<grid, 256, 0, s>>>((const float*)llr, numCb, llr_len, llr_stride, cfg->C, cfg->K,
                                                           cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, E0, nShort, fStep,

@@ -378,6 +378,115 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Staged scatter form of rateMatch (the one that normally runs).  The coded block is staged in shared memory as above;
+// the circular buffer is then walked in up to three segments (cut at k0 and at the filler gap) inside which the stream
+// index i = q + c and the source index n = q + d are affine in the buffer position q.  A warp takes 32*U consecutive
+// positions at a time; when they stay inside one row of the interleaver (same b = i / Eq) the rate-matched index
+// s*qm + b is affine too, so a byte costs one LDS.U8 + one STS.U8 (both conflict-free) into a shared-memory image of the
+// output slice, which is finally written with aligned 16-byte stores.  Chunks that straddle a row, the end of the data
+// or a repeated buffer (E > L) take the generic per-byte path.
+template <int U>
+__global__ void __launch_bounds__(256)
+    nr_rate_match_staged_kernel(const signed char* __restrict__ coded, long long numCb, int C, int N, int K, int F, int Z,
+                                int ncb, int k0, int qm, int E0, int nShort, int fStep, signed char* __restrict__ out,
+                                long long outStride, int ncbPad)
+{
+    extern __shared__ __align__(16) signed char rmSmem[];
+    signed char* cbS = rmSmem;
+    signed char* outS = rmSmem + ncbPad;
+    const int L = ncb - F;
+    const int sysLen = K - 2 * Z - F;
+    const int k0m = k0 % L;
+    const int nT = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nWarps = nT >> 5;
+    constexpr int CH = 32 * U;
+    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
+        const long long tb = cb / C;
+        const int r = (int)(cb - tb * C);
+        const int E = E0 + (r >= nShort ? fStep : 0);
+        const long long off = (long long)r * E0 + (long long)(r > nShort ? r - nShort : 0) * fStep;
+        const int Eq = E / qm;
+        const signed char* __restrict__ src = coded + cb * (long long)N;
+        signed char* __restrict__ dst = out + tb * outStride + off;
+        __syncthreads();   // the previous block's copy-out is done
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const int n16 = ncb >> 4;
+            const uint4* __restrict__ s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(cbS);
+#pragma unroll 2
+            for (int i = tid; i < n16; i += nT) d4[i] = __ldg(s4 + i);
+            for (int i = (n16 << 4) + tid; i < ncb; i += nT) cbS[i] = src[i];
+        } else {
+            for (int i = tid; i < ncb; i += nT) cbS[i] = src[i];
+        }
+        const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 15);
+        signed char* outB = outS + mis;   // outB[g] <-> dst[g]: 16-byte units of outS map to aligned units of the destination
+        __syncthreads();
+        // e[i] = circ[(k0 + i) mod L] (ldpc.py:1145-1151), out[s*qm + b] = e[b*Eq + s] (ldpc.py:1155)
+        auto emit = [&](int q, int c, int d) {
+            const signed char v = cbS[q + d];
+            for (int i = q + c; i < E; i += L) {
+                const int b = i / Eq, s2 = i - b * Eq;
+                outB[s2 * qm + b] = v;
+            }
+        };
+        auto seg = [&](int qlo, int qhi) {
+            if (qlo >= qhi) return;
+            const int c = (qlo < k0m) ? L - k0m : -k0m;
+            const int d = (qlo < sysLen) ? 0 : F;
+            const int qData = min(qhi, E - c);   // positions that are transmitted at least once
+            int qw = qlo + warp * CH;
+            if (qw >= qData) return;
+            int bw = (qw + c) / Eq, sw = (qw + c) - bw * Eq;   // interleaver row / column of the chunk's first position
+            const int step = nWarps * CH, stepB = step / Eq, stepS = step - stepB * Eq;
+            const bool noRep = E <= L;
+            for (; qw < qData; qw += step) {
+                if (noRep && qw + CH <= qData && sw + CH <= Eq) {
+                    const signed char* __restrict__ p = cbS + qw + d + lane;
+                    signed char* __restrict__ o = outB + (sw + lane) * qm + bw;
+                    signed char v[U];
+#pragma unroll
+                    for (int k = 0; k < U; k++) v[k] = p[32 * k];
+#pragma unroll
+                    for (int k = 0; k < U; k++) o[32 * k * qm] = v[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < U; k++) {
+                        const int q = qw + lane + 32 * k;
+                        if (q < qData) emit(q, c, d);
+                    }
+                }
+                sw += stepS;
+                bw += stepB;
+                if (sw >= Eq) {
+                    sw -= Eq;
+                    bw++;
+                }
+            }
+        };
+        const int cutA = min(k0m, sysLen), cutB = max(k0m, sysLen);
+        seg(0, cutA);
+        seg(cutA, cutB);
+        seg(cutB, L);
+        __syncthreads();
+        {   // copy-out: 16-byte units of outS; the first / last unit may be partial
+            const int nUnits = (mis + E + 15) >> 4;
+            const uint4* s4 = reinterpret_cast<const uint4*>(outS);
+            signed char* dstA = dst - mis;   // 16-byte aligned
+            for (int u = tid; u < nUnits; u += nT) {
+                const int g0 = 16 * u - mis;
+                if (g0 >= 0 && g0 + 16 <= E) {
+                    *reinterpret_cast<uint4*>(dstA + 16 * u) = s4[u];
+                } else {
+                    for (int k = 0; k < 16; k++) {
+                        const int g = g0 + k;
+                        if (g >= 0 && g < E) dst[g] = outB[g];
+                    }
+                }
+            }
+        }
+    }
+}
+
 void tb_split(const nrldpc_tb_config* c, int N, int* E0, int* nShort, int* fStep, int* k0)
 {
     const long long f = (long long)c->nl * c->qm;
@@ -482,6 +591,21 @@ extern "C" int nrldpc_rate_match(nrldpc_handle* h, const nrldpc_tb_config* cfg, 
     if (E0 % cfg->qm) { nr_set_error("rate_match: E not a multiple of qm"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
     const long long numCb = num_tb * cfg->C;
+    {   // staged scatter kernel: input block + output slice in shared memory
+        const int ncbPad = (cfg->ncb + 15) & ~15;
+        const size_t smemS = (size_t)ncbPad + (size_t)((E0 + fStep + 15) & ~15) + 32;
+        if (smemS <= (size_t)h->maxSmemOptin && E0 >= cfg->qm && !getenv("NRLDPC_RM_GENERIC")) {
+            int perSM = (int)((size_t)h->smemPerSM / (smemS + 1024));
+            perSM = perSM < 1 ? 1 : (perSM > 8 ? 8 : perSM);
+            const int gridS = (int)min(numCb, (long long)h->numSMs * perSM);
+            if (smemS > 48 * 1024) NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_match_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS));
+            nr_rate_match_staged_kernel<4><<<gridS, 256, smemS, (cudaStream_t)stream>>>((const signed char*)coded, numCb, cfg->C, N, cfg->K,
+                                                                                  cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, E0, nShort, fStep,
+                                                                                  (signed char*)out, out_stride, ncbPad);
+            NR_CUDA_CHECK(cudaGetLastError());
+            return NRLDPC_OK;
+        }
+    }
     const int grid = (int)min(numCb, (long long)h->numSMs * 8);
     const size_t smem = (size_t)((cfg->ncb + 15) & ~15);
     if (smem > 48 * 1024) NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
