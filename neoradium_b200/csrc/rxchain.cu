@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256)
 // conflict-free LDS, one add and one coalesced store per element, no index arithmetic.  Positions that receive more
 // than one LLR (E > L: repetition) add their further terms in ascending stream order, as the reference's chunked `+=`.
 template <typename T, bool SB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512, 4)
     nr_rate_recover_staged_kernel(const T* __restrict__ llr, long long numCb, long long llrLen, long long llrStride, int C,
                                   int K, int F, int Z, int ncb, int k0, int qm, uint32_t qmMagic, int E0, int nShort,
                                   int fStep, T* softBuf, T* __restrict__ out)
@@ -168,8 +168,10 @@ extern "C" int nrldpc_rate_recover(nrldpc_handle* h, const nrldpc_tb_config* cfg
     const bool staged = (dtype == NRLDPC_F32 || dtype == NRLDPC_F64) && smem <= (size_t)h->maxSmemOptin &&
                         ((uintptr_t)llr & 15) == 0 && E0 >= cfg->qm && !getenv("NRLDPC_RR_GENERIC");
     if (staged) {
+        const char* thr = getenv("NRLDPC_RR_THREADS");   // A/B measurements
+        const int nThr = thr ? atoi(thr) : 512;            // 4 CTAs x 512 threads fill an SM (32 registers per thread)
         int perSM = (int)((size_t)h->smemPerSM / (smem + 1024));
-        perSM = perSM < 1 ? 1 : (perSM > 8 ? 8 : perSM);
+        perSM = perSM < 1 ? 1 : (perSM > 2048 / nThr ? 2048 / nThr : perSM);
         const int grid = (int)min(numCb, (long long)h->numSMs * perSM);
         const uint32_t magic = cfg->qm > 1 ? (uint32_t)((0x100000000ULL + (uint64_t)cfg->qm - 1) / (uint64_t)cfg->qm) : 0u;
 #define NR_RR_LAUNCH(T, SBF)                                                                                          \
@@ -177,7 +179,7 @@ extern "C" int nrldpc_rate_recover(nrldpc_handle* h, const nrldpc_tb_config* cfg
         if (smem > 48 * 1024)                                                                                         \
             NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_recover_staged_kernel<T, SBF>,                                 \
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));              \
-        nr_rate_recover_staged_kernel<T, SBF><<<grid, 256, smem, s>>>((const T*)llr, numCb, llr_len, llr_stride, cfg->C, \
+        nr_rate_recover_staged_kernel<T, SBF><<<grid, nThr, smem, s>>>((const T*)llr, numCb, llr_len, llr_stride, cfg->C, \
                                                                       cfg->K, cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, \
                                                                       magic, E0, nShort, fStep, (T*)soft_buffer,      \
                                                                       (T*)out);                                       \

@@ -365,6 +365,26 @@ def test_wraparound_and_lbrm_recover():
             assert np.array_equal(got, want) and np.array_equal(h.decBuffer, buf)
 
 
+def test_rate_match_repetition_and_lbrm():
+    """rateMatch with E > Ncb - F (the circular buffer is sent more than once), LBRM buffers and every rv, C == 1 and
+    C > 1: the staged scatter kernel's generic path (chunks that straddle interleaver rows / repeated buffers)."""
+    rng = np.random.default_rng(12)
+    for bg, A, mod, g, nref, nl in [(2, 100, 'BPSK', 5000, 0, 1), (2, 60, 'QPSK', 7000, 0, 1), (1, 2400, 'QPSK', 4800, 5000, 1),
+                                    (2, 1000, '16QAM', 40000, 0, 1), (1, 9000, '64QAM', 60000, 0, 2), (2, 4000, '1024QAM', 30000, 0, 1),
+                                    (1, 20000, '256QAM', 90000, 12000, 1)]:
+        qm = O.MOD_ORDER[mod]
+        enc = LdpcEncoder(bg, mod, nl, nref, 0.5)
+        tb = rng.integers(0, 2, A).astype(np.int8)
+        cbs = enc.doSegmentation(enc.appendCrc(tb, '24A'))
+        ocbs, p = O.segment(O.crc_attach(tb, '24A'), bg)
+        coded = enc.encode(cbs)
+        ocoded = O.encode(ocbs, bg, p['Zc'], p['iLS'])
+        assert np.array_equal(coded, ocoded)
+        for rv in range(4):
+            assert np.array_equal(enc.rateMatch(coded, g, True, rv),
+                                  O.rate_match(ocoded, bg, p['Zc'], p['K'], p['F'], g, qm, nl, nref, rv)), (bg, A, mod, rv)
+
+
 def test_error_behaviour_on_gpu():
     dec = LdpcDecoder(1, 'QPSK')
     h = Harq()
