@@ -699,7 +699,9 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     if (staticRows) miscBytes += 16 + 16 + 64 * sizeof(uint32_t) + (size_t)a.packWords * sizeof(uint32_t);
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
-    int occ = h->decOcc > 0 ? h->decOcc : ((oneCb && sizeof(T) == 4) ? 2 : 1);
+    // (measured at 17 scheduled rows, profiles/r01_decode_per_lifting_size.json: two resident CTAs lift the generic fp32
+    // kernels by 11-45 %, a third one helps only the 7-8 warp CTAs of Zc = 208 / 240)
+    int occ = h->decOcc > 0 ? h->decOcc : (sizeof(T) == 4 ? ((!oneCb && a.cbPerCta == 1 && nT <= 256) ? 3 : 2) : 1);
     occ = max(1, min(occ, 2048 / nT));
     if (sizeof(T) == 8) occ = 1;
     // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs

@@ -599,10 +599,21 @@ extern "C" int nrldpc_rate_match(nrldpc_handle* h, const nrldpc_tb_config* cfg, 
             int perSM = (int)((size_t)h->smemPerSM / (smemS + 1024));
             perSM = perSM < 1 ? 1 : (perSM > 2048 / nThr ? 2048 / nThr : perSM);
             const int gridS = (int)min(numCb, (long long)h->numSMs * perSM);
-            if (smemS > 48 * 1024) NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_match_staged_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemS));
-            nr_rate_match_staged_kernel<4><<<gridS, nThr, smemS, (cudaStream_t)stream>>>((const signed char*)coded, numCb, cfg->C, N, cfg->K,
-                                                                                  cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, E0, nShort, fStep,
-                                                                                  (signed char*)out, out_stride, ncbPad);
+            const char* ue = getenv("NRLDPC_RM_U");   // A/B measurements: positions per lane per chunk
+            const int U = ue ? atoi(ue) : 4;
+#define NR_RM_LAUNCH(UU)                                                                                                \
+    do {                                                                                                                \
+        if (smemS > 48 * 1024)                                                                                          \
+            NR_CUDA_CHECK(cudaFuncSetAttribute(nr_rate_match_staged_kernel<UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smemS));                                                            \
+        nr_rate_match_staged_kernel<UU><<<gridS, nThr, smemS, (cudaStream_t)stream>>>(                                   \
+            (const signed char*)coded, numCb, cfg->C, N, cfg->K, cfg->F, cfg->zc, cfg->ncb, k0, cfg->qm, E0, nShort, fStep, \
+            (signed char*)out, out_stride, ncbPad);                                                                     \
+    } while (0)
+            if (U == 8) NR_RM_LAUNCH(8);
+            else if (U == 2) NR_RM_LAUNCH(2);
+            else NR_RM_LAUNCH(4);
+#undef NR_RM_LAUNCH
             NR_CUDA_CHECK(cudaGetLastError());
             return NRLDPC_OK;
         }
