@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     uint32_t* pk = crcRed + 64;   // bit-packed hard decisions of the early-termination test (a.packWords words)
     float* stage = reinterpret_cast<float*>(pk + ((SBG != 0) ? a.packWords : 0));
     const bool useStage = (SBG != 0) && a.stageFloats > 0;
-    LayerBar lb;
+    LayerBarT<(ALLT ? NR_DEC_BAR_MODE : 0)> lb;
     lb.bar = barLayer;
     lb.phase = 0;
     uint32_t stagePhase = 0;

@@ -549,13 +549,18 @@ struct BgRows {
 // overlaps the barrier latency instead of following it.
 //   mode 0: plain bar.sync at the wait point   mode 1: mbarrier, one arrival per warp   mode 2: hardware cluster
 //   barrier of the (implicit 1-CTA) cluster, which is split-phase by construction
+// Measured on B200 (BG1 Zc=384): for the all-Tensor-Memory kernels (every scheduled row's state in TMEM, the R >= ~0.5 case
+// of the benchmark) mode 1 is +0.7 % over mode 0 (19.76 vs 19.63 Gbit/s), for the kernels whose state spills to shared-memory
+// planes / the L2 scratch (low rates, all 46 rows) it is 5-8 % SLOWER (731 vs 775 G edge-updates/s): the mode is a template
+// parameter chosen per kernel.  Mode 2 is slower everywhere.
 #ifndef NR_DEC_BAR_MODE
-#define NR_DEC_BAR_MODE 1   // measured on B200 (BG1 Zc=384, 1024 blocks, r1j): mode 1 +0.5-0.8 % over mode 0 now that gathers sit between arrive and wait; mode 2 slower
+#define NR_DEC_BAR_MODE 1   // mode of the all-TMEM kernels; the others use mode 0
 #endif
-struct LayerBar {
+template <int MODE>
+struct LayerBarT {
     uint32_t bar;     // shared-memory address of the mbarrier (mode 1)
     uint32_t phase;
-    static constexpr int mode = NR_DEC_BAR_MODE;
+    static constexpr int mode = MODE;
     __device__ __forceinline__ void arrive() const
     {
         if (mode == 1) {
@@ -632,7 +637,7 @@ __device__ __forceinline__ void pregather_row(const char* rb, RowCtx<T, BG, ROW>
         if ((PRE >> j) & 1u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.pre[j]) : "r"(rbS + c.off[j]));
 }
 
-template <typename T, int BG, int ROW, typename Store>
+template <typename T, int BG, int ROW, typename Store, typename LayerBar>
 __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
                                                 RowCtx<T, BG, ROW>& cur, uint32_t* pe)
