@@ -704,6 +704,10 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     int occ = h->decOcc > 0 ? h->decOcc : (sizeof(T) == 4 ? ((!oneCb && a.cbPerCta == 1 && nT <= 256) ? 3 : 2) : 1);
     occ = max(1, min(occ, 2048 / nT));
     if (sizeof(T) == 8) occ = 1;
+    // static fp32 kernels: when the scheduled rows fit Tensor Memory only with ONE resident CTA (22-42 rows: low code rates,
+    // every BG2 row), one all-TMEM CTA per SM beats two CTAs whose state spills to shared-memory planes / the L2 scratch
+    // (measured: BG2 all rows 635 -> 773, 30 rows BG1 705 -> 775 G edge-updates/s); beyond 42 rows two spilling CTAs win
+    if (staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
     // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs
     a.tmemRows = 0;
     a.tmemCols = 0;
