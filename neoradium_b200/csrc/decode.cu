@@ -32,7 +32,10 @@ namespace {
 // three-tier state storage: rows [0, tmemRows) in Tensor Memory (ONE_CB kernels), the next smemRows rows in shared
 // memory planes, the rest in the per-CTA global scratch (stays in L2).  All branches are on the (uniform) row index.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool ONE_CB, bool ALLT>
+//   ALLT = 1: every scheduled row in Tensor Memory (no tier branches);  ALLT = 2 ("split"): rows [0, kSplitRows) in Tensor
+//   Memory at the same fixed stride, every further scheduled row in the shared-memory planes -- the tier of a row is then
+//   known at compile time in the static schedule (22-33 scheduled rows with two resident CTAs, i.e. code rates ~0.4-0.54)
+template <typename T, bool ONE_CB, int ALLT>
 struct StateStore {
     uint32_t tbase;     // this thread's TMEM address of row slot 0 (lane quadrant and warp column offset folded in)
     uint32_t tstride;   // TMEM columns per row slot
@@ -42,10 +45,16 @@ struct StateStore {
     // ALLT: every scheduled row lives in Tensor Memory at a compile-time stride (3 warps per lane quadrant): no tier
     // branches, and with a static row index the TMEM address is base + immediate
     static constexpr uint32_t kAllTStride = 3u * (sizeof(T) == 4 ? 4u : 8u);   // referenced by the ALLT instantiations only
+    static constexpr int kSplitRows = 21;   // 256 TMEM columns / kAllTStride (fp32)
     __device__ __forceinline__ void load(int row, RowState<T>& st) const
     {
-        if constexpr (ALLT) {
+        if constexpr (ALLT == 1) {
             tmem_ld(st, tbase + (uint32_t)row * kAllTStride);
+            return;
+        }
+        if constexpr (ALLT == 2) {
+            if (row < kSplitRows) tmem_ld(st, tbase + (uint32_t)row * kAllTStride);
+            else load_state(st, sS + (size_t)(row - kSplitRows) * NPLANES * nT, nT);
             return;
         }
         if (ONE_CB && row < tmemRows)
@@ -57,8 +66,13 @@ struct StateStore {
     }
     __device__ __forceinline__ void store(int row, const RowState<T>& st) const
     {
-        if constexpr (ALLT) {
+        if constexpr (ALLT == 1) {
             tmem_st(st, tbase + (uint32_t)row * kAllTStride);
+            return;
+        }
+        if constexpr (ALLT == 2) {
+            if (row < kSplitRows) tmem_st(st, tbase + (uint32_t)row * kAllTStride);
+            else store_state(st, sS + (size_t)(row - kSplitRows) * NPLANES * nT, nT);
             return;
         }
         if (ONE_CB && row < tmemRows)
@@ -98,7 +112,7 @@ __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
 // the kernel.  ONE_CB: exactly one code block per CTA and blockDim.x == Z (Z a multiple of 32): no thread is ever
 // idle, so the row bodies run in convergent code and the (column, shift) table is read through the uniform datapath.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool ONE_CB, int SBG, bool ALLT>
+template <typename T, bool ONE_CB, int SBG, int ALLT>
 __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     {
         const int warp = tid >> 5;
         const uint32_t RW = sizeof(T) == 4 ? 4u : 8u;
-        const uint32_t wpq = ALLT ? 3u : ((uint32_t)((nT >> 5) + 3) >> 2);   // warps per lane quadrant
+        const uint32_t wpq = ALLT != 0 ? 3u : ((uint32_t)((nT >> 5) + 3) >> 2);   // warps per lane quadrant
         store.tstride = wpq * RW;
         store.tbase = useTmem ? (tmemBaseSh + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * RW) : 0u;   // lane (warp%4)*32 in bits 31..16
         store.sS = stateS + tid;
@@ -172,7 +186,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     uint32_t* pk = crcRed + 64;   // bit-packed hard decisions of the early-termination test (a.packWords words)
     float* stage = reinterpret_cast<float*>(pk + ((SBG != 0) ? a.packWords : 0));
     const bool useStage = (SBG != 0) && a.stageFloats > 0;
-    LayerBarT<(ALLT ? NR_DEC_BAR_MODE : 0)> lb;
+    LayerBarT<(ALLT == 1 ? NR_DEC_BAR_MODE : (ALLT == 2 ? NR_DEC_BAR_MODE_SPLIT : 0))> lb;
     lb.bar = barLayer;
     lb.phase = 0;
     uint32_t stagePhase = 0;
@@ -707,7 +721,14 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // static fp32 kernels: when the scheduled rows fit Tensor Memory only with ONE resident CTA (22-42 rows: low code rates,
     // every BG2 row), one all-TMEM CTA per SM beats two CTAs whose state spills to shared-memory planes / the L2 scratch
     // (measured: BG2 all rows 635 -> 773, 30 rows BG1 705 -> 775 G edge-updates/s); beyond 42 rows two spilling CTAs win
-    if (staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
+    // ... unless the rows beyond the 21 that fit 256 TMEM columns fit the shared-memory planes of two resident CTAs: the
+    // "split" kernels keep both CTAs and know every row's tier at compile time
+    bool split = false;
+    if (staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
+        const size_t budget2 = min((size_t)h->smemPerSM / 2 - 1024, (size_t)h->maxSmemOptin);
+        split = rBytes + miscBytes + (size_t)(a.numRows - 21) * rowBytes <= budget2;
+    }
+    if (!split && staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
     // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs
     a.tmemRows = 0;
     a.tmemCols = 0;
@@ -722,6 +743,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
             allT = true;
             wpq = 3;
         }
+        if (split) wpq = 3;   // 21 rows at the fixed stride
         int rowsFit = cols / (wpq * RW);
         if (rowsFit > a.numRows) rowsFit = a.numRows;
         if (rowsFit > 0) {
@@ -806,17 +828,20 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         return cudaSuccess;
     };
     constexpr int S1 = sizeof(T) == 4 ? 1 : 0, S2 = sizeof(T) == 4 ? 2 : 0;   // static schedules exist in fp32 only
-    constexpr bool AT = sizeof(T) == 4;
+    constexpr int AT = sizeof(T) == 4 ? 1 : 0, SP = sizeof(T) == 4 ? 2 : 0;
+    if (split && (a.tmemRows != 21 || a.smemRows != a.numRows - 21)) { nr_set_error("decode: internal error (split state layout)"); return NRLDPC_ERR_ARG; }
     if (staticRows && g.P == NR_BG1_ROWS) {
-        if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT>));
-        else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, false>));
+        if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP>));
+        else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT>));
+        else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, 0>));
     } else if (staticRows) {
-        if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT>));
-        else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, false>));
+        if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP>));
+        else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT>));
+        else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, 0>));
     } else if (oneCb) {
-        NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, 0, false>));
+        NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, 0, 0>));
     } else {
-        NR_CUDA_CHECK(launch(nr_decode_kernel<T, false, 0, false>));
+        NR_CUDA_CHECK(launch(nr_decode_kernel<T, false, 0, 0>));
     }
     NR_CUDA_CHECK(cudaGetLastError());
     return NRLDPC_OK;

@@ -556,6 +556,9 @@ struct BgRows {
 #ifndef NR_DEC_BAR_MODE
 #define NR_DEC_BAR_MODE 1   // mode of the all-TMEM kernels; the others use mode 0
 #endif
+#ifndef NR_DEC_BAR_MODE_SPLIT
+#define NR_DEC_BAR_MODE_SPLIT 0   // mode of the split (TMEM + shared planes) kernels
+#endif
 template <int MODE>
 struct LayerBarT {
     uint32_t bar;     // shared-memory address of the mbarrier (mode 1)

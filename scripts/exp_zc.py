@@ -12,7 +12,8 @@ res = {}
 for bg, n, k, edges in ((1, 68, 22, 316), (2, 52, 10, 197)):
     for zc in [int(v) for v in os.environ.get('ZCS', '384,352,320,256,240,208,192,176,128,96,64,32,16,8').split(',')]:
         numCb = max(2048, min(65536, (1 << 24) // (n * zc)))
-        x = torch.randn((numCb, (n - 2) * zc), device='cuda') * 2 + 1.5
+        f64 = os.environ.get('DT', 'f32') == 'f64'   # DT=f64: the float64 instantiation (the drop-in default precision)
+        x = torch.randn((numCb, (n - 2) * zc), device='cuda', dtype=torch.float64 if f64 else torch.float32) * 2 + 1.5
         rows = int(os.environ.get('ROWS', '0'))
         flags = 2
         if rows:
@@ -25,7 +26,7 @@ for bg, n, k, edges in ((1, 68, 22, 316), (2, 52, 10, 197)):
         bits = torch.empty((numCb, k * zc), dtype=torch.int8, device='cuda')
         s = _dev.stream_ptr()
         def run():
-            _native.check(L.nrldpc_decode(h, bg, zc, _native.F32, _native.F32, _dev.ptr(x), numCb, (n - 2) * zc, n - 2, 8, flags, k,
+            _native.check(L.nrldpc_decode(h, bg, zc, _native.F64 if f64 else _native.F32, _native.F64 if f64 else _native.F32, _dev.ptr(x), numCb, (n - 2) * zc, n - 2, 8, flags, k,
                                           _dev.ptr(bits), None, None, s))
         run(); run(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

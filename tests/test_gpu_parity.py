@@ -145,6 +145,8 @@ CHAIN_CASES = [
     (1, 3000, '64QAM', 0.5, 1, 2), (2, 300, 'QPSK', 0.25, 1, 3), (1, 1200, '16QAM', 0.4, 2, 0), (2, 100, 'BPSK', 0.2, 1, 0),
     (2, 40, 'QPSK', 0.2, 1, 1), (1, 500, '256QAM', 0.7, 1, 0), (1, 20000, '256QAM', 0.8, 4, 1), (2, 3800, '1024QAM', 0.5, 1, 0),
     (1, 8424 * 3 - 24, '16QAM', 1 / 3, 1, 0), (2, 9000, 'QPSK', 0.2, 1, 0), (2, 12, 'QPSK', 0.2, 1, 0), (1, 30, 'QPSK', 0.34, 1, 0),
+    # 22-33 scheduled rows at Zc = 384 / 256: the split (Tensor Memory + shared planes) static decoder kernels
+    (1, 8424 * 2 - 24, 'QPSK', 0.45, 1, 0), (2, 3816, '16QAM', 0.3, 1, 0), (1, 5608, '64QAM', 0.42, 1, 0),
 ]
 
 
@@ -275,7 +277,10 @@ def test_early_stop_parity_protocol():
 
 
 @pytest.mark.parametrize("bg,A,mod,rate,numTb", [(2, 500, 'QPSK', 0.3, 23), (1, 600, '16QAM', 0.5, 40), (2, 24, 'QPSK', 0.25, 130),
-                                                  (1, 20000, '64QAM', 0.75, 5), (1, 2000, 'QPSK', 0.4, 9)])
+                                                  (1, 20000, '64QAM', 0.75, 5), (1, 2000, 'QPSK', 0.4, 9),
+                                                  # static kernels, 22-33 scheduled rows (split state: TMEM + shared planes)
+                                                  (1, 8424 * 2 - 24, '16QAM', 0.48, 5), (2, 3816, 'QPSK', 0.3, 7),
+                                                  (1, 5608, '16QAM', 0.45, 6)])
 def test_batched_codec_small_z_multi_cb_per_cta(bg, A, mod, rate, numTb):
     """Batches of equally configured TBs: several code blocks share a CTA at small Zc, last group partially filled."""
     rng = np.random.default_rng(A)
