@@ -112,7 +112,8 @@ __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
 // the kernel.  ONE_CB: exactly one code block per CTA and blockDim.x == Z (Z a multiple of 32): no thread is ever
 // idle, so the row bodies run in convergent code and the (column, shift) table is read through the uniform datapath.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, bool ONE_CB, int SBG, int ALLT>
+// ESM (static kernels): 1 = the early-termination code is compiled in (run-time flag), 0 = left out altogether
+template <typename T, bool ONE_CB, int SBG, int ALLT, int ESM = 1>
 __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
@@ -459,8 +460,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             if constexpr (SBG != 0) {
                 RowCtx<T, SBG, 0> c0;
                 prep_row<T, SBG, 0>(g, mU, ZB, store, dummyOff, c0);
-                run_rows_static<T, SBG, 0>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0,
-                                           (a.flags & NRLDPC_DEC_EARLY_STOP) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr);
+                run_rows_static<T, SBG, 0, (ESM != 0)>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0,
+                                                       (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr);
             } else {
                 for (int row = 0; row < a.numRows; row++) {
                     if (ONE_CB || (active && !cbDone)) {
@@ -474,7 +475,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             }
             if (!cbDone) itersDone = it + 1;
             if constexpr (SBG != 0) {
-                if (a.flags & NRLDPC_DEC_EARLY_STOP) {
+                if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) {
                     // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed: every warp ballots the sign
                     // of its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
                     // neighbouring words); the scheduled extension columns were packed by their rows (run_rows_static); then one thread
@@ -829,13 +830,19 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     };
     constexpr int S1 = sizeof(T) == 4 ? 1 : 0, S2 = sizeof(T) == 4 ? 2 : 0;   // static schedules exist in fp32 only
     constexpr int AT = sizeof(T) == 4 ? 1 : 0, SP = sizeof(T) == 4 ? 2 : 0;
+    // the all-TMEM / split kernels exist with and without the early-termination code (its mere presence costs the row loop a few %)
+    const bool noEs = sizeof(T) == 4 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && !getenv("NRLDPC_ES_CODE");
     if (split && (a.tmemRows != 21 || a.smemRows != a.numRows - 21)) { nr_set_error("decode: internal error (split state layout)"); return NRLDPC_ERR_ARG; }
     if (staticRows && g.P == NR_BG1_ROWS) {
-        if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP>));
+        if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP, 0>));
+        else if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP>));
+        else if (allT && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT, 0>));
         else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT>));
         else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, 0>));
     } else if (staticRows) {
-        if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP>));
+        if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP, 0>));
+        else if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP>));
+        else if (allT && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT, 0>));
         else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT>));
         else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, 0>));
     } else if (oneCb) {

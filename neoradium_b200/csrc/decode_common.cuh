@@ -640,14 +640,14 @@ __device__ __forceinline__ void pregather_row(const char* rb, RowCtx<T, BG, ROW>
         if ((PRE >> j) & 1u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.pre[j]) : "r"(rbS + c.off[j]));
 }
 
-template <typename T, int BG, int ROW, typename Store, typename LayerBar>
+template <typename T, int BG, int ROW, bool ES, typename Store, typename LayerBar>
 __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
                                                 RowCtx<T, BG, ROW>& cur, uint32_t* pe)
 {
     constexpr int D = BgRows<BG>::deg(ROW);
     process_row_at<T, D, (ROW >= 4), pregather_mask<BG, ROW>()>(cur.off, rb, cur.st, slot, dummyOff, g.onef, true, (T)0.75, cur.pre);
-    if constexpr (ROW >= 4) {
+    if constexpr (ES && ROW >= 4) {
         if (pe) {   // early termination: packed hard decisions of this row's private extension column (see the kernel)
             const uint32_t w = __ballot_sync(0xffffffffu, FP<T>::sign(cur.st.rext) != 0);
             if ((threadIdx.x & 31) == 0) pe[(ROW - 4) * (blockDim.x >> 5) + (threadIdx.x >> 5)] = w;
@@ -664,7 +664,7 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
         prep_row<T, BG, ROW + 1>(g, m, ZB, store, dummyOff, nxt);
         if constexpr (sizeof(T) == 4) pregather_row<T, BG, ROW + 1>(rb, nxt);
         lb.wait();
-        run_rows_static<T, BG, ROW + 1>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
+        run_rows_static<T, BG, ROW + 1, ES>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
     } else {
         lb.wait();
     }
