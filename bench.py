@@ -408,7 +408,7 @@ def run_ours(args):
     lane_rate = 148 * 128 * sm_mhz * 1e6                       # issue slots x 32 lanes per second at the sampled clock
     edge_rate = ncb * EDGE_UPDATES_PER_CB / (kern_ms * 1e-3)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": 58.66e6 * ncb / 1024.0, "traffic_source": "profiles/r01_decode_ncu_metrics.csv (ncu --set full, r1j): dram read 57.65 MB + write 1.01 MB per 1024-block launch",
+                "traffic": 58.26e6 * ncb / 1024.0, "traffic_source": "profiles/r01_decode_ncu_metrics.csv (ncu --set full, r1m): dram read 57.70 MB + write 0.56 MB per 1024-block launch",
                 "kernel": "nr_decode_kernel<float, ONE_CB>", "kernel_ms": kern_ms,
                 "kernel_ms_source": "CUDA events around each launch of the single-stream pass (launches do not overlap there)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",

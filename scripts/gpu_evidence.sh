@@ -12,5 +12,9 @@ timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 # helper kernels, config 4 (early termination), per-lifting-size throughput
 for NTB in 256 1024; do NTB=$NTB timeout 300 python scripts/bench_kernels.py > gpurun_out/helpers_$NTB.json 2>/dev/null; done
 timeout 600 python scripts/exp_cfg4.py 2>&1 | tail -7
-timeout 600 python scripts/exp_zc.py > gpurun_out/exp_zc.log 2>&1
+OUT=exp_zc_allrows.json timeout 600 python scripts/exp_zc.py > gpurun_out/exp_zc_allrows.log 2>&1
+ROWS=17 OUT=exp_zc_rows17.json timeout 600 python scripts/exp_zc.py > gpurun_out/exp_zc_rows17.log 2>&1
+timeout 300 python scripts/exp_rate.py > gpurun_out/exp_rate.log 2>&1
+# one ncu --set full capture of every helper kernel (profiles/r01_helper_ncu_metrics.csv)
+timeout 900 bash scripts/ncu_helpers.sh r1
 tail -c 600 gpurun_out/bench.json
