@@ -141,7 +141,7 @@ def run_reference(args):
                                        "core, through the NumPy oracle port of recoverRate->decode(8)->checkCrcAndMerge->"
                                        "checkCrc (float64, the reference's arithmetic)" % (cores, cores * C_PER_TB)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -456,12 +456,31 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps, "gpu_launches_all_timed_regions": 2 * args.steps * 2 + 8 * args.steps * 3,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "check": {"tb_crc_ok": tb_ok, "tbs": tbs, "payload_bit_errors": bit_err, "two_stream_tb_crc_ok": pipe_ok}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the run, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (e.g. NCCL's version banner under torchrun)
+    # is sent to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
