@@ -113,7 +113,8 @@ __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
 // idle, so the row bodies run in convergent code and the (column, shift) table is read through the uniform datapath.
 // ---------------------------------------------------------------------------------------------------------------
 // ESM (static kernels): 1 = the early-termination code is compiled in (run-time flag), 0 = left out altogether
-template <typename T, bool ONE_CB, int SBG, int ALLT, int ESM = 1>
+//      ZS (static kernels without the early-termination code): lifting size known at compile time (SpecTab), 0 = run time
+template <typename T, bool ONE_CB, int SBG, int ALLT, int ESM = 1, int ZS = 0>
 __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
@@ -459,8 +460,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         for (int it = 0; it < a.numIter; it++) {
             if constexpr (SBG != 0) {
                 RowCtx<T, SBG, 0> c0;
-                prep_row<T, SBG, 0>(g, mU, ZB, store, dummyOff, c0);
-                run_rows_static<T, SBG, 0, (ESM != 0)>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0,
+                prep_row<T, SBG, 0, ZS>(g, mU, ZB, store, dummyOff, c0);
+                run_rows_static<T, SBG, 0, (ESM != 0), ZS>(g, a.numRows, rb, mU, ZB, store, slot, dummyOff, lb, c0,
                                                        (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr);
             } else {
                 for (int row = 0; row < a.numRows; row++) {
@@ -831,16 +832,24 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     constexpr int S1 = sizeof(T) == 4 ? 1 : 0, S2 = sizeof(T) == 4 ? 2 : 0;   // static schedules exist in fp32 only
     constexpr int AT = sizeof(T) == 4 ? 1 : 0, SP = sizeof(T) == 4 ? 2 : 0;
     // the all-TMEM / split kernels exist with and without the early-termination code (its mere presence costs the row loop a few %)
+    constexpr int Z384 = sizeof(T) == 4 ? 384 : 0;
+    // compile-time edge table (SpecTab) for the largest lifting size: no uniform table loads in front of a row, +2-3 %
+    // (bench 20.07 -> 20.67 Gbit/s)
+    const bool z384 = sizeof(T) == 4 && Z == 384 && !getenv("NRLDPC_NO_SPECZ");
     const bool noEs = sizeof(T) == 4 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && !getenv("NRLDPC_ES_CODE");
     if (split && (a.tmemRows != 21 || a.smemRows != a.numRows - 21)) { nr_set_error("decode: internal error (split state layout)"); return NRLDPC_ERR_ARG; }
     if (staticRows && g.P == NR_BG1_ROWS) {
-        if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP, 0>));
+        // (the BG1 split kernel spills with the compile-time table -- 861 vs 914 G edge-updates/s -- and keeps the run-time one)
+        if (allT && noEs && z384) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT, 0, Z384>));
+        else if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP, 0>));
         else if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, SP>));
         else if (allT && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT, 0>));
         else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, AT>));
         else NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S1, 0>));
     } else if (staticRows) {
-        if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP, 0>));
+        if (split && noEs && z384) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP, 0, Z384>));
+        else if (allT && noEs && z384) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT, 0, Z384>));
+        else if (split && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP, 0>));
         else if (split) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, SP>));
         else if (allT && noEs) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT, 0>));
         else if (allT) NR_CUDA_CHECK(launch(nr_decode_kernel<T, true, S2, AT>));

@@ -542,6 +542,41 @@ struct BgRows {
     }
 };
 
+// Compile-time copy of the decoder's edge table (build_dec_graph<float>) for ONE lifting size ZS: with the static schedule
+// the two table words of an edge become immediates of the address IMADs -- no uniform constant loads in front of a row.
+// Instantiated for ZS = 384 (the largest lifting size: the throughput case); ZS = 0 means "run-time table".
+template <int BG, int ZS>
+struct SpecTab {
+    static __host__ __device__ constexpr int ils()
+    {
+        int a = ZS;
+        while (a % 2 == 0 && a > 2) a /= 2;   // ZS = a * 2^j, a in {2, 3, 5, 7, 9, 11, 13, 15}
+        return a == 2 ? 0 : a == 3 ? 1 : a == 5 ? 2 : a == 7 ? 3 : a == 9 ? 4 : a == 11 ? 5 : a == 13 ? 6 : 7;
+    }
+    static constexpr uint32_t S = (uint32_t)((0x100000000ULL + (unsigned long long)(ZS > 0 ? ZS : 1) - 1) / (unsigned long long)(ZS > 0 ? ZS : 1));
+    static __host__ __device__ constexpr uint32_t col(int e) { return BG == 1 ? NR_BG1_COL[e] : NR_BG2_COL[e]; }
+    static __host__ __device__ constexpr uint32_t shift(int e)
+    {
+        return (uint32_t)((BG == 1 ? NR_BG1_SHIFT[ils()][e] : NR_BG2_SHIFT[ils()][e]) % (ZS > 0 ? ZS : 1));
+    }
+    static __host__ __device__ constexpr uint32_t x(int e) { return (uint32_t)((unsigned long long)shift(e) * S); }   // mod 2^32
+    static __host__ __device__ constexpr uint32_t y(int e) { return col(e) * (uint32_t)ZS * 4u; }
+};
+template <int BG, int ROW, int ZS, int J, int D>
+__device__ __forceinline__ void row_offsets_spec_step(uint32_t m, Lift L, uint32_t dummyOff, uint32_t (&off)[D])
+{
+    if constexpr (J < D) {
+        constexpr int e = BgRows<BG>::e0(ROW) + J;
+        if constexpr (ROW >= 4 && J == D - 1) {
+            off[J] = dummyOff;
+        } else {
+            constexpr uint32_t X = SpecTab<BG, ZS>::x(e), Y = SpecTab<BG, ZS>::y(e);
+            off[J] = lifted_offset(m, L, make_uint2(X, Y));
+        }
+        row_offsets_spec_step<BG, ROW, ZS, J + 1, D>(m, L, dummyOff, off);
+    }
+}
+
 // Split layer barrier.  The posteriors written by layer i are read by other threads in layer i+1, so the layers of a
 // code block are separated by a CTA-wide barrier -- but everything a thread does between its last posterior store of
 // layer i and its first gather of layer i+1 is private (row state to Tensor Memory, next row's state back, the lifted
@@ -622,12 +657,15 @@ __host__ __device__ constexpr uint32_t pregather_mask()
 #endif
 }
 
-template <typename T, int BG, int ROW, typename Store>
+template <typename T, int BG, int ROW, int ZS = 0, typename Store>
 __device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift ZB, const Store& store,
                                          uint32_t dummyOff, RowCtx<T, BG, ROW>& c)
 {
     store.load(ROW, c.st);
-    row_offsets<BgRows<BG>::deg(ROW), (ROW >= 4)>(g, BgRows<BG>::e0(ROW), m, ZB, dummyOff, c.off);
+    if constexpr (ZS != 0)
+        row_offsets_spec_step<BG, ROW, ZS, 0, BgRows<BG>::deg(ROW)>(m, ZB, dummyOff, c.off);
+    else
+        row_offsets<BgRows<BG>::deg(ROW), (ROW >= 4)>(g, BgRows<BG>::e0(ROW), m, ZB, dummyOff, c.off);
 }
 
 template <typename T, int BG, int ROW>
@@ -640,7 +678,7 @@ __device__ __forceinline__ void pregather_row(const char* rb, RowCtx<T, BG, ROW>
         if ((PRE >> j) & 1u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.pre[j]) : "r"(rbS + c.off[j]));
 }
 
-template <typename T, int BG, int ROW, bool ES, typename Store, typename LayerBar>
+template <typename T, int BG, int ROW, bool ES, int ZS = 0, typename Store, typename LayerBar>
 __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
                                                 const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
                                                 RowCtx<T, BG, ROW>& cur, uint32_t* pe)
@@ -661,10 +699,10 @@ __device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows
             return;
         }
         RowCtx<T, BG, ROW + 1> nxt;
-        prep_row<T, BG, ROW + 1>(g, m, ZB, store, dummyOff, nxt);
+        prep_row<T, BG, ROW + 1, ZS>(g, m, ZB, store, dummyOff, nxt);
         if constexpr (sizeof(T) == 4) pregather_row<T, BG, ROW + 1>(rb, nxt);
         lb.wait();
-        run_rows_static<T, BG, ROW + 1, ES>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
+        run_rows_static<T, BG, ROW + 1, ES, ZS>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
     } else {
         lb.wait();
     }
