@@ -245,6 +245,35 @@ def test_row_skipping_flag_is_exact():
         assert np.array_equal(res[0][1], (want < 0).astype(np.int8)) and np.array_equal(res[1][1], res[0][1])
 
 
+def test_decoder_kernel_variants_agree(monkeypatch):
+    """Every static fp32 kernel variant a configuration can be routed to (compile-time edge table for Zc=384, with / without the
+    early-termination code, split vs single all-TMEM CTA vs tiered state, forced residency) returns the oracle's beliefs bit for
+    bit.  The library reads these knobs at every launch."""
+    rng = np.random.default_rng(33)
+    knobs = [{}, {"NRLDPC_NO_SPECZ": "1"}, {"NRLDPC_ES_CODE": "1"}, {"NRLDPC_NO_SPLIT": "1"}, {"NRLDPC_NO_SPLIT": "1", "NRLDPC_NO_SPECZ": "1"},
+             {"NRLDPC_NO_SPECZ": "1", "NRLDPC_ES_CODE": "1"}]
+    for bg, zc, rows in [(1, 384, 17), (1, 384, 26), (2, 384, 26), (2, 384, 42), (1, 320, 24), (1, 384, 40), (1, 384, 46)]:
+        _, n, k = O.bg_dims(bg)
+        ils = O.set_index_of(zc)
+        C = 3
+        cw = O.encode(rng.integers(0, 2, (C, k * zc)).astype(np.int8), bg, zc, ils)
+        llr = ((1 - 2.0 * cw) * 3 + 2.4 * rng.standard_normal(cw.shape)).astype(np.float32)
+        llr[:, (k + rows - 2) * zc:] = 0           # `rows` scheduled rows
+        want = OC.decode_beliefs(llr, bg, zc, ils, 4, np.float32)
+        x = torch.from_numpy(llr).cuda()
+        for kn in knobs:
+            with monkeypatch.context() as mp:
+                for name, val in kn.items():
+                    mp.setenv(name, val)
+                bel = torch.empty((C, n * zc), dtype=torch.float32, device='cuda')
+                bits = torch.empty((C, n * zc), dtype=torch.int8, device='cuda')
+                _native.check(_native.lib().nrldpc_decode(_dev.handle(), bg, zc, _native.F32, _native.F32, _dev.ptr(x), C,
+                                                          (n - 2) * zc, n - 2, 4, 0, n, _dev.ptr(bits), _dev.ptr(bel),
+                                                          None, _dev.stream_ptr()))
+                assert np.array_equal(bel.cpu().numpy(), want), (bg, zc, rows, kn)
+                assert np.array_equal(bits.cpu().numpy(), (want < 0).astype(np.int8)), (bg, zc, rows, kn)
+
+
 def test_early_stop_parity_protocol():
     """Early termination is an extension: the kernel reports the per-block iteration count n, and the block's output
     must equal the oracle run with numIter = n; a stopped block satisfies every parity check."""
