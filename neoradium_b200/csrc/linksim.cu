@@ -132,80 +132,99 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
     }
     return ctr;
 }
-// two independent N(0,1) values from two 32-bit words (Box-Muller; u1 in (0,1] keeps the tail to 6.7 sigma)
+// two independent N(0,1) values from two 32-bit words (Box-Muller; u1 in (0,1] keeps the tail to 6.7 sigma).  The noise
+// only has to be Gaussian, not bit-reproducible against another implementation, so the logarithm and the sine / cosine
+// are the SFU approximations (absolute error ~2^-21 on these ranges; checked by test_awgn_generator_statistics_*).
 __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b)
 {
     const float u1 = (float)a * 2.3283064365386963e-10f + 1.1641532182693481e-10f;   // (a + 0.5) / 2^32
-    const float u2 = (float)b * 2.3283064365386963e-10f;
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float ang = (float)b * 1.4629180792671596e-9f;                              // 2 pi b / 2^32
+    const float r = sqrtf(-2.0f * __logf(u1));
     float sn, cs;
-    sincospif(2.0f * u2, &sn, &cs);
+    __sincosf(ang, &sn, &cs);
     return make_float2(r * cs, r * sn);
 }
 
 // Fused transmit-channel-receive for workload generation: bits -> Gray QAM -> + CN(0, noiseVar) -> max-log LLR (fp32).
-// Symbol n of the call draws its noise from Philox counter (offset + n) under `seed`: the result does not depend on the
+// Symbol n of the call has the absolute index a = offset + n and draws its noise from Philox counter a >> 1 under `seed`
+// (words 0,1 for even a, words 2,3 for odd a: one Philox call serves two symbols): the result does not depend on the
 // launch geometry, and a sweep sharded over GPUs / batches stays reproducible by passing the global symbol offset.
-// SPT symbols per thread so that a thread's LLRs fill whole float4 stores.
+// A thread owns SPT (even) symbols that start at an even absolute index, so that its LLRs fill whole float4 stores.
 template <int QM, int SPT>
 __global__ void __launch_bounds__(LS_THREADS)
     nr_awgn_llr_kernel(const signed char* __restrict__ bits, long long numSym, float noiseVar, unsigned long long seed,
                        unsigned long long offset, float* __restrict__ llr)
 {
+    static_assert(SPT % 2 == 0, "pairs of symbols share one Philox call");
     constexpr int HALF = QM / 2;
-    constexpr int NLL = QM * SPT;       // LLRs per thread (multiple of 4 whenever the stream length allows)
+    constexpr int NLL = QM * SPT;       // LLRs per thread
     __shared__ float levels[32];
     if (QM > 1 && (int)threadIdx.x < (1 << HALF)) levels[threadIdx.x] = (float)qam_scale(QM) * (float)pam_level(threadIdx.x, HALF);
     __syncthreads();
     const float scale = (float)qam_scale(QM);
     const float sigma = sqrtf(0.5f * noiseVar);
     const float invN0 = 1.0f / noiseVar;
-    const long long numGroups = (numSym + SPT - 1) / SPT;
-    const bool vec = ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && (NLL % 4 == 0);
+    const long long o1 = (long long)(offset & 1ull);      // symbol n sits at shifted index n + o1 (same parity as a)
+    const unsigned long long pair0 = offset >> 1;         // Philox counter of shifted indices 0, 1
+    const long long numGroups = (numSym + o1 + SPT - 1) / SPT;
+    const bool vec = ((reinterpret_cast<uintptr_t>(llr) & 15) == 0) && (NLL % 4 == 0) && ((o1 * QM) % 4 == 0);
+    const bool bitsWord = (QM % 4 == 0) && ((reinterpret_cast<uintptr_t>(bits) & 3) == 0);
     for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < numGroups;
          gidx += (long long)gridDim.x * blockDim.x) {
         float o[NLL];
 #pragma unroll
-        for (int k = 0; k < SPT; k++) {
-            const long long s = gidx * SPT + k;
-            if (s < numSym) {
-                uint32_t v = 0;
+        for (int k2 = 0; k2 < SPT; k2 += 2) {
+            const unsigned long long c = pair0 + (unsigned long long)((gidx * SPT + k2) >> 1);
+            const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 #pragma unroll
-                for (int i = 0; i < QM; i++) v = (v << 1) | (uint32_t)(bits[s * QM + i] & 1);
-                int re, im;
-                qam_point(v, QM, re, im);
-                const unsigned long long c = offset + (unsigned long long)s;
-                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
-                                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-                const float2 nz = box_muller(rnd.x, rnd.y);
-                const float yr = scale * (float)re + sigma * nz.x, yi = scale * (float)im + sigma * nz.y;
-                if (QM == 1) {
-                    const float a = scale;
-                    const float d0 = (yr - a) * (yr - a) + (yi - a) * (yi - a), d1 = (yr + a) * (yr + a) + (yi + a) * (yi + a);
-                    o[k] = (d1 - d0) * invN0;
-                } else {
-                    float lr[HALF > 0 ? HALF : 1], li[HALF > 0 ? HALF : 1];
-                    axis_llr<float, (HALF > 0 ? HALF : 1)>(yr, HALF, levels, invN0, lr);
-                    axis_llr<float, (HALF > 0 ? HALF : 1)>(yi, HALF, levels, invN0, li);
+            for (int h = 0; h < 2; h++) {
+                const int k = k2 + h;
+                const long long s = gidx * SPT + k - o1;
+                if (s >= 0 && s < numSym) {
+                    uint32_t v = 0;
+                    if (bitsWord) {   // labels of QM = 4 | 8 bits as whole words: byte i of a word is bit i (MSB first)
 #pragma unroll
-                    for (int p = 0; p < HALF; p++) {
-                        o[k * QM + 2 * p] = lr[p];
-                        o[k * QM + 2 * p + 1] = li[p];
+                        for (int wd = 0; wd < QM / 4; wd++) {
+                            const uint32_t w = reinterpret_cast<const uint32_t*>(bits)[s * (QM / 4) + wd];
+                            v = (v << 4) | (((w & 0x01010101u) * 0x08040201u) >> 24);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < QM; i++) v = (v << 1) | (uint32_t)(bits[s * QM + i] & 1);
                     }
-                }
-            } else {
+                    int re, im;
+                    qam_point(v, QM, re, im);
+                    const float2 nz = h ? box_muller(rnd.z, rnd.w) : box_muller(rnd.x, rnd.y);
+                    const float yr = scale * (float)re + sigma * nz.x, yi = scale * (float)im + sigma * nz.y;
+                    if (QM == 1) {
+                        const float a = scale;
+                        const float d0 = (yr - a) * (yr - a) + (yi - a) * (yi - a), d1 = (yr + a) * (yr + a) + (yi + a) * (yi + a);
+                        o[k] = (d1 - d0) * invN0;
+                    } else {
+                        float lr[HALF > 0 ? HALF : 1], li[HALF > 0 ? HALF : 1];
+                        axis_llr<float, (HALF > 0 ? HALF : 1)>(yr, HALF, levels, invN0, lr);
+                        axis_llr<float, (HALF > 0 ? HALF : 1)>(yi, HALF, levels, invN0, li);
 #pragma unroll
-                for (int i = 0; i < QM; i++) o[k * QM + i] = 0.f;
+                        for (int p = 0; p < HALF; p++) {
+                            o[k * QM + 2 * p] = lr[p];
+                            o[k * QM + 2 * p + 1] = li[p];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < QM; i++) o[k * QM + i] = 0.f;
+                }
             }
         }
-        const long long base = gidx * NLL;
-        if (vec && (gidx + 1) * SPT <= numSym) {
+        const long long base = (gidx * SPT - o1) * QM;   // may be negative for the first group when the offset is odd
+        if (vec && gidx * SPT - o1 >= 0 && (gidx + 1) * SPT - o1 <= numSym) {
 #pragma unroll
             for (int q4 = 0; q4 < NLL / 4; q4++)
                 reinterpret_cast<float4*>(llr + base)[q4] = make_float4(o[4 * q4], o[4 * q4 + 1], o[4 * q4 + 2], o[4 * q4 + 3]);
         } else {
             for (int i = 0; i < NLL; i++)
-                if (base + i < numSym * QM) llr[base + i] = o[i];
+                if (base + i >= 0 && base + i < numSym * QM) llr[base + i] = o[i];
         }
     }
 }
@@ -262,16 +281,16 @@ extern "C" int nrldpc_awgn_llr(nrldpc_handle* h, int qm, const int8_t* bits, int
     const float nv = (float)noise_var;
 #define NR_LAUNCH_AWGN(QM, SPT)                                                                               \
     {                                                                                                          \
-        const long long groups = (num_sym + (SPT)-1) / (SPT);                                                  \
+        const long long groups = (num_sym + 1 + (SPT)-1) / (SPT);                                              \
         const int grid = (int)min((groups + LS_THREADS - 1) / LS_THREADS, (long long)h->numSMs * 16);          \
         nr_awgn_llr_kernel<QM, SPT><<<grid, LS_THREADS, 0, s>>>(b, num_sym, nv, seed, offset, llr);            \
     }
     switch (qm) {
         case 1: NR_LAUNCH_AWGN(1, 4) break;
         case 2: NR_LAUNCH_AWGN(2, 2) break;
-        case 4: NR_LAUNCH_AWGN(4, 1) break;
+        case 4: NR_LAUNCH_AWGN(4, 2) break;
         case 6: NR_LAUNCH_AWGN(6, 2) break;
-        case 8: NR_LAUNCH_AWGN(8, 1) break;
+        case 8: NR_LAUNCH_AWGN(8, 2) break;
         default: NR_LAUNCH_AWGN(10, 2) break;
     }
 #undef NR_LAUNCH_AWGN
