@@ -48,6 +48,10 @@ enum {
     NRLDPC_DEC_EARLY_STOP = 1,  /* extension: stop a code block once all parity checks hold after a full iteration */
     NRLDPC_DEC_ALL_ROWS = 2     /* disable the (exact) skipping of extension rows whose parity LLRs are all zero */
 };
+/* with NRLDPC_DEC_EARLY_STOP: bits 8..15 of `flags` hold the first iteration (1-based) after which the syndrome is tested;
+ * 0 or 1 = after every iteration.  A block then runs at least that many iterations (results per returned iteration count
+ * are unchanged: they equal a fixed-iteration decode with that count). */
+#define NRLDPC_DEC_ES_FROM(k) ((((k) < 0 ? 0 : (k) > 255 ? 255 : (k)) & 0xff) << 8)
 
 int nrldpc_version(void);
 const char* nrldpc_last_error(void);

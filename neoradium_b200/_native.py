@@ -28,6 +28,11 @@ F32, F64, F16 = 0, 1, 2
 DEC_EARLY_STOP, DEC_ALL_ROWS = 1, 2
 
 
+def dec_flags(early_stop, es_from=1):
+    """decoder flags word: NRLDPC_DEC_EARLY_STOP | NRLDPC_DEC_ES_FROM(es_from) (include/nrldpc.h)"""
+    return (DEC_EARLY_STOP | ((max(0, min(255, int(es_from))) & 0xff) << 8)) if early_stop else 0
+
+
 class NrldpcError(RuntimeError):
     pass
 

@@ -34,7 +34,7 @@ class PendingDecode:
 
 class TbBatchCodec:
     def __init__(self, baseGraphNo, modulation, txBlockSize, g, txLayers=1, nRef=0, rv=0, precision='fp32',
-                 earlyStop=False, device=None, ownHandle=False):
+                 earlyStop=False, device=None, ownHandle=False, earlyStopFrom=1):
         """``ownHandle=True`` gives the codec a private library handle (scratch, temporaries): required when several
         codecs issue work concurrently on DIFFERENT streams (include/nrldpc.h: one handle per (device, stream))."""
         if baseGraphNo not in (1, 2):
@@ -56,6 +56,7 @@ class TbBatchCodec:
         self.sumE = int(sum(self.lens))
         self.precision = precision
         self.earlyStop = earlyStop
+        self.earlyStopFrom = earlyStopFrom   # first iteration after which the syndrome is tested (extension, default: every one)
         self.device = device if device is not None else _dev.device()
         self.cfg = _native.TbConfig(bg=self.bg, zc=self.Zc, K=self.K, F=self.F, C=self.C, qm=self.qm, nl=self.nl,
                                     ncb=self.ncb, rv=self.rv, reserved=0, G=self.G)
@@ -96,7 +97,7 @@ class TbBatchCodec:
         numTb = llr.shape[0]
         if out is None:
             out = self.alloc_outputs(numTb)
-        flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
+        flags = _native.dec_flags(self.earlyStop, self.earlyStopFrom)
         _native.check(_native.lib().nrldpc_decode_tb(
             self._h, self.cfg, _IN_DTYPE[llr.dtype],
             _native.F64 if self.precision == 'fp64' else _native.F32, _dev.ptr(llr), numTb, llr.shape[1],

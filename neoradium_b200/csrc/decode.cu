@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             }
             if (!cbDone) itersDone = it + 1;
             if constexpr (SBG != 0) {
-                if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) {
+                if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= ((a.flags >> 8) & 0xff)) {
                     // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed: every warp ballots the sign
                     // of its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
                     // neighbouring words); the scheduled extension columns were packed by their rows (run_rows_static); then one thread
@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                     if (!anyBad) break;
                 }
             } else
-            if (a.flags & NRLDPC_DEC_EARLY_STOP) {
+            if ((a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= ((a.flags >> 8) & 0xff)) {
                 // syndrome of the hard decisions after a COMPLETE iteration over the scheduled rows (skipped rows are
                 // satisfied by construction: their parity bit is the parity of the rest)
                 uint32_t bad = 0;

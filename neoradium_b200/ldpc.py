@@ -10,7 +10,8 @@ Extensions (all opt-in, defaults reproduce the reference):
     evaluated in float32 -- the throughput mode the benchmarks use)
   * ``LdpcDecoder.decodeLLRs(llrs, txBlockSize, numIter, harq=None)``: the fused chain of harq.py:165-173 in one
     kernel, for one transport block or a batch ([numTb, G]) of equally configured ones
-  * ``earlyStop``  stop a code block once all parity checks hold (the reference always runs numIter iterations)
+  * ``earlyStop``  stop a code block once all parity checks hold (the reference always runs numIter iterations);
+    ``earlyStopFrom=k`` tests the syndrome from iteration k on (a block runs at least k iterations)
 Deliberate deviations ("do not copy"): the base graph is re-derived whenever (Zc, iLS) change
 (the reference caches a stale one, ldpc.py:777) and ``isValidCodedBlock`` checks all rows (ldpc.py:841-843 returns
 after the first).
@@ -282,12 +283,14 @@ class _PendingLLRs:
 class LdpcDecoder(LdpcBase):
     """LDPC decoder: rate recovery, layered min-sum decoding, CRC check and merge (neoradium/ldpc.py:1220-1619)."""
 
-    def __init__(self, baseGraphNo=1, modulation='QPSK', txLayers=1, nRef=0, precision='fp64', earlyStop=False):
+    def __init__(self, baseGraphNo=1, modulation='QPSK', txLayers=1, nRef=0, precision='fp64', earlyStop=False,
+                 earlyStopFrom=1):
         super().__init__(baseGraphNo, modulation, txLayers, nRef)
         if precision not in _TORCH_F:
             raise ValueError("'precision' must be 'fp64' or 'fp32'!")
         self.precision = precision
         self.earlyStop = earlyStop
+        self.earlyStopFrom = earlyStopFrom   # with earlyStop: first iteration after which the syndrome is tested
         self.lastIterations = None      # per-code-block iteration counts of the last decode (extension)
         self.rowStarts = None           # reference attributes of the undocumented decode2 (ldpc.py:1287-1290)
         self.rowNZcounts = None
@@ -363,7 +366,7 @@ class LdpcDecoder(LdpcBase):
         else:
             bits = torch.empty((c, outCols * z), dtype=torch.int8, device=x.device)
         iters = torch.empty((c,), dtype=torch.int32, device=x.device)
-        flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
+        flags = _native.dec_flags(self.earlyStop, self.earlyStopFrom)
         _native.check(_native.lib().nrldpc_decode(
             _dev.handle(), self.baseGraphNo, z, _native.F64 if in64 else _native.F32, _NATIVE_F[self.precision],
             _dev.ptr(x), c, nIn, n - 2, int(numIter), flags, outCols, _dev.ptr(bits), _dev.ptr(beliefs),
@@ -460,11 +463,11 @@ class LdpcDecoder(LdpcBase):
                 hdt in (torch.float32, torch.float64, torch.float16, np.float32, np.float64, np.float16):
             from .batch import TbBatchCodec
             x = llrs if isT else np.ascontiguousarray(llrs)
-            key = (txBlockSize, x.shape[1], precision, self.earlyStop)
+            key = (txBlockSize, x.shape[1], precision, self.earlyStop, self.earlyStopFrom)
             codec = getattr(self, '_hostCodec', None)
             if codec is None or self._hostCodecKey != key:
                 codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, x.shape[1], self.txLayers, self.nRef,
-                                     0, precision, self.earlyStop)
+                                     0, precision, self.earlyStop, earlyStopFrom=self.earlyStopFrom)
                 self._hostCodec, self._hostCodecKey = codec, key
             def unpack(res):
                 self.lastIterations = res['iters'].numpy().reshape(-1)
@@ -498,7 +501,7 @@ class LdpcDecoder(LdpcBase):
         cbOk = torch.empty((numTb, c), dtype=torch.uint8, device=x.device)
         tbOk = torch.empty((numTb,), dtype=torch.uint8, device=x.device)
         iters = torch.empty((numTb, c), dtype=torch.int32, device=x.device)
-        flags = _native.DEC_EARLY_STOP if self.earlyStop else 0
+        flags = _native.dec_flags(self.earlyStop, self.earlyStopFrom)
         _native.check(_native.lib().nrldpc_decode_tb(
             _dev.handle(), cfg, {torch.float64: _native.F64, torch.float16: _native.F16}.get(x.dtype, _native.F32),
             _NATIVE_F[precision], _dev.ptr(x), numTb, G, x.stride(0), _dev.ptr(buf), int(numIter), flags, _dev.ptr(tb), c * per,

@@ -16,7 +16,7 @@ for snr in (10.5, 9.0, 8.6):
     pl = torch.randint(0, 2, (tbs, A), dtype=torch.int8, device=dev, generator=gen)
     llr = awgn_llr(codec0.encode(pl), 4, snr_db=snr, seed=77, offset=0)
     for es in (False, True):
-        codec = TbBatchCodec(1, "16QAM", A, G, precision="fp32", earlyStop=es, device=dev)
+        codec = TbBatchCodec(1, "16QAM", A, G, precision="fp32", earlyStop=es, device=dev, earlyStopFrom=int(os.environ.get("ES_FROM", "1")))   # ES_FROM=k: test the syndrome from iteration k on
         out = codec.alloc_outputs(tbs)
         for _ in range(2):
             codec.decode(llr, 8, out=out)

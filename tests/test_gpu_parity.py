@@ -4,6 +4,8 @@ float64 beliefs; fp32 beliefs are compared bit-for-bit against the fp32 evaluati
 1e-4 tolerance of north_star is therefore slack, asserted as exact equality)."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -303,6 +305,26 @@ def test_early_stop_parity_protocol():
                 if n_it > 1:   # and it had NOT converged one iteration earlier
                     prev = (OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, n_it - 1, np.float32) < 0).astype(np.int8)
                     assert not O.parity_ok(prev[0], bg, 384, 1)
+    # earlyStopFrom = k: the syndrome is tested from iteration k on -- blocks that converged earlier report k, the others are unchanged,
+    # and every output still equals the fixed-iteration decode with the reported count (static and generic kernels)
+    for kw, zc_case in (({}, None), ({"precision": "fp32"}, "generic")):
+        k = int(np.median(iters))
+        c2 = TbBatchCodec(bg, '16QAM', A, g, precision='fp32', earlyStop=True, earlyStopFrom=k)
+        if zc_case == "generic":
+            os.environ["NRLDPC_NO_STATIC_ROWS"] = "1"
+            c2 = TbBatchCodec(bg, '16QAM', A, g, precision='fp32', earlyStop=True, earlyStopFrom=k, ownHandle=True)
+        try:
+            out2 = c2.decode(llr, 12)
+            it2 = out2["iters"].cpu().numpy().reshape(-1)
+        finally:
+            os.environ.pop("NRLDPC_NO_STATIC_ROWS", None)
+        assert np.array_equal(it2, np.maximum(iters, k))
+        tb2 = out2["tb"].cpu().numpy()
+        for t in range(numTb):
+            rr, _, p = O.rate_recover(llr_h[t], A, bg, 4, dtype=np.float32)
+            for r in range(2):
+                hard = (OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, int(it2[t * 2 + r]), np.float32) < 0).astype(np.int8)
+                assert np.array_equal(tb2[t, r * codec.per:(r + 1) * codec.per], hard[0, :codec.per])
 
 
 @pytest.mark.parametrize("bg,A,mod,rate,numTb", [(2, 500, 'QPSK', 0.3, 23), (1, 600, '16QAM', 0.5, 40), (2, 24, 'QPSK', 0.25, 130),
