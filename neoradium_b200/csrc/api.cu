@@ -127,6 +127,8 @@ extern "C" int nrldpc_destroy(nrldpc_handle* h)
     if (h->tmp2) cudaFree(h->tmp2);
     if (h->goldTables) cudaFree(h->goldTables);
     if (h->crcFacDev) cudaFree(h->crcFacDev);
+    if (h->tbAcc) cudaFree(h->tbAcc);
+    if (h->tbFacDev) cudaFree(h->tbFacDev);
     if (h->workCounter) cudaFree(h->workCounter);
     free(h);
     return NRLDPC_OK;

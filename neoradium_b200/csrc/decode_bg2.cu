@@ -1,0 +1,5 @@
+// Statically scheduled fp32 decoder kernels, BG2, without the early-termination code (decode_inst.cuh).
+#define NR_INST_NAME nr_launch_static_bg2
+#define NR_INST_BG 2
+#define NR_INST_ES 0
+#include "decode_inst.cuh"

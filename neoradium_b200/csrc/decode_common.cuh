@@ -57,7 +57,11 @@ struct DecArgs {
     signed char* tbBits;
     long long tbBitsStride;
     unsigned char* cbCrcOk;
-    unsigned int* cbRemA;    // per-CB CRC24A remainder of its payload (combined per TB by a second kernel)
+    // transport-block CRC24A, combined inside the kernel: every block XORs  remA_r * x^(per (C-1-r)) mod g  into tbAcc[2 tb]
+    // and counts itself in tbAcc[2 tb + 1]; the block that completes the count writes tbOk[tb] and clears both words
+    unsigned int* tbAcc;          // [numTb][2], all zero between launches
+    const unsigned int* tbFac;    // [C]: x^(per (C-1-r)) mod g24A
+    unsigned char* tbOk;
     // overflow state
     void* scratch;
     unsigned int* workCounter;
@@ -562,21 +566,6 @@ struct SpecTab {
     static __host__ __device__ constexpr uint32_t x(int e) { return (uint32_t)((unsigned long long)shift(e) * S); }   // mod 2^32
     static __host__ __device__ constexpr uint32_t y(int e) { return col(e) * (uint32_t)ZS * 4u; }
 };
-template <int BG, int ROW, int ZS, int J, int D>
-__device__ __forceinline__ void row_offsets_spec_step(uint32_t m, Lift L, uint32_t dummyOff, uint32_t (&off)[D])
-{
-    if constexpr (J < D) {
-        constexpr int e = BgRows<BG>::e0(ROW) + J;
-        if constexpr (ROW >= 4 && J == D - 1) {
-            off[J] = dummyOff;
-        } else {
-            constexpr uint32_t X = SpecTab<BG, ZS>::x(e), Y = SpecTab<BG, ZS>::y(e);
-            off[J] = lifted_offset(m, L, make_uint2(X, Y));
-        }
-        row_offsets_spec_step<BG, ROW, ZS, J + 1, D>(m, L, dummyOff, off);
-    }
-}
-
 // Split layer barrier.  The posteriors written by layer i are read by other threads in layer i+1, so the layers of a
 // code block are separated by a CTA-wide barrier -- but everything a thread does between its last posterior store of
 // layer i and its first gather of layer i+1 is private (row state to Tensor Memory, next row's state back, the lifted
@@ -625,88 +614,6 @@ struct LayerBarT {
         }
     }
 };
-
-template <typename T, int BG, int ROW>
-struct RowCtx {   // what a thread prepares for a row before it may touch the posteriors
-    static constexpr int D = BgRows<BG>::deg(ROW);
-    uint32_t off[D];
-    RowState<T> st;
-    float pre[D];   // posteriors gathered ahead of the barrier (edges of pregather_mask)
-};
-
-// Edges of row ROW whose column is NOT an edge of row ROW - 1: the previous layer does not write them, and every older
-// write is already ordered by an earlier barrier, so they may be gathered BEFORE the barrier that ends row ROW - 1.
-// Row 0 follows the last scheduled row of the previous iteration (a run-time quantity): nothing is pre-gathered there.
-template <int BG, int ROW>
-__host__ __device__ constexpr uint32_t pregather_mask()
-{
-#if NR_DEC_PREGATHER
-    if (ROW == 0) return 0u;
-    const int e0 = BgRows<BG>::e0(ROW), d = BgRows<BG>::deg(ROW) - (ROW >= 4 ? 1 : 0);
-    const int p0 = BgRows<BG>::e0(ROW > 0 ? ROW - 1 : 0), pd = BgRows<BG>::deg(ROW > 0 ? ROW - 1 : 0);
-    uint32_t mask = 0;
-    for (int j = 0; j < d; j++) {
-        const int col = BG == 1 ? NR_BG1_COL[e0 + j] : NR_BG2_COL[e0 + j];
-        bool hit = false;
-        for (int k = 0; k < pd; k++) hit = hit || ((BG == 1 ? NR_BG1_COL[p0 + k] : NR_BG2_COL[p0 + k]) == col);
-        if (!hit) mask |= 1u << j;
-    }
-    return mask;
-#else
-    return 0u;
-#endif
-}
-
-template <typename T, int BG, int ROW, int ZS = 0, typename Store>
-__device__ __forceinline__ void prep_row(const NrDecGraph& g, uint32_t m, Lift ZB, const Store& store,
-                                         uint32_t dummyOff, RowCtx<T, BG, ROW>& c)
-{
-    store.load(ROW, c.st);
-    if constexpr (ZS != 0)
-        row_offsets_spec_step<BG, ROW, ZS, 0, BgRows<BG>::deg(ROW)>(m, ZB, dummyOff, c.off);
-    else
-        row_offsets<BgRows<BG>::deg(ROW), (ROW >= 4)>(g, BgRows<BG>::e0(ROW), m, ZB, dummyOff, c.off);
-}
-
-template <typename T, int BG, int ROW>
-__device__ __forceinline__ void pregather_row(const char* rb, RowCtx<T, BG, ROW>& c)
-{
-    constexpr uint32_t PRE = pregather_mask<BG, ROW>();
-    const uint32_t rbS = (uint32_t)__cvta_generic_to_shared(rb);
-#pragma unroll
-    for (int j = 0; j < BgRows<BG>::deg(ROW); j++)
-        if ((PRE >> j) & 1u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(c.pre[j]) : "r"(rbS + c.off[j]));
-}
-
-template <typename T, int BG, int ROW, bool ES, int ZS = 0, typename Store, typename LayerBar>
-__device__ __forceinline__ void run_rows_static(const NrDecGraph& g, int numRows, char* rb, uint32_t m, Lift ZB,
-                                                const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
-                                                RowCtx<T, BG, ROW>& cur, uint32_t* pe)
-{
-    constexpr int D = BgRows<BG>::deg(ROW);
-    process_row_at<T, D, (ROW >= 4), pregather_mask<BG, ROW>()>(cur.off, rb, cur.st, slot, dummyOff, g.onef, true, (T)0.75, cur.pre);
-    if constexpr (ES && ROW >= 4) {
-        if (pe) {   // early termination: packed hard decisions of this row's private extension column (see the kernel)
-            const uint32_t w = __ballot_sync(0xffffffffu, FP<T>::sign(cur.st.rext) != 0);
-            if ((threadIdx.x & 31) == 0) pe[(ROW - 4) * (blockDim.x >> 5) + (threadIdx.x >> 5)] = w;
-        }
-    }
-    lb.arrive();
-    store.store(ROW, cur.st);
-    if constexpr (ROW + 1 < BgRows<BG>::P) {
-        if (ROW + 1 >= 4 && ROW + 1 >= numRows) {   // numRows >= 4 always
-            lb.wait();
-            return;
-        }
-        RowCtx<T, BG, ROW + 1> nxt;
-        prep_row<T, BG, ROW + 1, ZS>(g, m, ZB, store, dummyOff, nxt);
-        if constexpr (sizeof(T) == 4) pregather_row<T, BG, ROW + 1>(rb, nxt);
-        lb.wait();
-        run_rows_static<T, BG, ROW + 1, ES, ZS>(g, numRows, rb, m, ZB, store, slot, dummyOff, lb, nxt, pe);
-    } else {
-        lb.wait();
-    }
-}
 
 // posterior addressed by edge `e` for lifted index m
 template <typename T>
@@ -838,8 +745,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t phase)
 }
 
 // host: byte-offset edge table for compute type T
+// taggedTab: the table of the static kernels (decode_static.cuh): x = (column << 16) | shift * sizeof(T), y = column * (Z * sizeof(T) - 65536)
 template <typename T>
-void build_dec_graph(const NrGraph& g, NrDecGraph* d)
+void build_dec_graph(const NrGraph& g, NrDecGraph* d, bool taggedTab = false)
 {
     memset(d, 0, sizeof(*d));
     d->P = g.P; d->ncols = g.ncols; d->ksys = g.ksys; d->ncore = g.ncore; d->Z = g.Z;
@@ -849,8 +757,13 @@ void build_dec_graph(const NrGraph& g, NrDecGraph* d)
     d->S = (uint32_t)((0x100000000ULL + (uint64_t)g.Z - 1) / (uint64_t)g.Z);   // ceil(2^32 / Z); Z >= 2
     for (int e = 0; e < g.rowEdge0[g.P]; e++) {
         const uint32_t col = g.edge[e] >> 16, sh = g.edge[e] & 0xffffu;
-        d->tab[e].x = (uint32_t)((uint64_t)sh * d->S);   // mod 2^32
-        d->tab[e].y = col * g.Z * (uint32_t)sizeof(T);
+        if (taggedTab) {
+            d->tab[e].x = (col << 16) | (sh * (uint32_t)sizeof(T));
+            d->tab[e].y = col * ((uint32_t)g.Z * (uint32_t)sizeof(T) - 65536u);   // mod 2^32
+        } else {
+            d->tab[e].x = (uint32_t)((uint64_t)sh * d->S);   // mod 2^32
+            d->tab[e].y = col * g.Z * (uint32_t)sizeof(T);
+        }
         d->raw[e] = (uint16_t)((col << 9) | sh);
     }
 }

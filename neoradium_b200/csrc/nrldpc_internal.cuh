@@ -36,6 +36,11 @@ struct nrldpc_handle {
     size_t tmp2Bytes;
     void* crcFacDev;        // cached per-thread CRC factors of the fused decoder epilogue (decode.cu), key below
     unsigned long long crcFacKey;
+    void* tbAcc;            // per-transport-block CRC24A accumulators of the fused decoder (decode.cu), zero between launches
+    size_t tbAccBytes;
+    void* tbFacDev;         // cached x^(per (C-1-r)) mod g24A of the fused decoder, key below
+    unsigned long long tbFacKey;
+    size_t tbFacCap;
     void* goldTables;       // device copy of the Gold-sequence jump tables (linksim.cu), created on first use
     int smemPerSM;
     int decOcc;             // target resident decoder CTAs per SM (0 = automatic), env NRLDPC_DEC_OCC

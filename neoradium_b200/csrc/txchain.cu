@@ -496,7 +496,11 @@ void tb_split(const nrldpc_tb_config* c, int N, int* E0, int* nShort, int* fStep
     *nShort = (int)(c->C - gBase % c->C);
     static const int k0n1[4] = {0, 17, 33, 56}, k0n2[4] = {0, 13, 25, 43};
     const int num = (c->bg == 1 ? k0n1 : k0n2)[c->rv];
+    // start of the reads in the filler-less circular buffer, reduced once here: (arange + start) % cirBufSize of
+    // ldpc.py:1148/1407 lets start exceed the buffer (LBRM + small BG2 block + rv 3: k0 >= Ncb - F)
+    const int L = c->ncb - c->F;
     *k0 = (int)(((long long)num * c->ncb / N) * c->zc);
+    if (L > 0) *k0 %= L;
 }
 
 }   // namespace

@@ -421,6 +421,63 @@ def test_wraparound_and_lbrm_recover():
             assert np.array_equal(got, want) and np.array_equal(h.decBuffer, buf)
 
 
+def test_lbrm_small_bg2_start_beyond_buffer():
+    """LBRM + small BG2 block (kb = 6: F >= 4 Zc) + rv 3: the start k0 of the reads lies BEYOND the filler-less circular
+    buffer (k0 >= Ncb - F), which the reference wraps with (arange + start) % cirBufSize (ldpc.py:1148, 1407).  TX, the
+    stand-alone rate recovery, and the fused decode (with and without a soft buffer, fp32 and fp64) must all agree with
+    the oracle."""
+    rng = np.random.default_rng(31)
+
+    def rx_chain_lbrm(llr, A, bg, qm, nit, nref, rv, soft, dt):
+        # O.rx_chain with the rate-recovered LLRs zero-extended to N (the reference's decode asserts on an LBRM-shortened
+        # array, ldpc.py:1539; the fused chain treats the columns beyond Ncb as not received, i.e. LLR 0)
+        rr, buf, p = O.rate_recover(llr, A, bg, qm, 1, nref, rv, soft, dt)
+        N = (66 if bg == 1 else 50) * p["Zc"]
+        rr = np.concatenate([rr, np.zeros((rr.shape[0], N - rr.shape[1]), dt)], axis=1)
+        bits = O.decode(rr, bg, p["Zc"], p["iLS"], nit, dtype=dt)
+        tbm, cb_ok = O.check_crc_and_merge(bits, p["K"], p["F"], p["C"])
+        return tbm[:-24], cb_ok, bool(O.crc_check(tbm, "24A")), buf, p
+
+    for A, nref, g in [(100, 400, 600), (150, 300, 420), (60, 300, 1000), (100, 600, 300)]:
+        bg, mod, qm = 2, 'QPSK', 2
+        p0 = O.derive_params(bg, A + 24)
+        zc, K = p0["Zc"], p0["K"]
+        F = K - (A + 24)
+        ncb = min(50 * zc, nref)
+        assert O.k0_start(bg, 3, ncb, 50 * zc, zc) >= ncb - F          # the case under test
+        enc = LdpcEncoder(bg, mod, 1, nref, 0.3)
+        tb = rng.integers(0, 2, A).astype(np.int8)
+        coded = enc.encode(enc.doSegmentation(enc.appendCrc(tb, '24A')))
+        ocbs, p = O.segment(O.crc_attach(tb, '24A'), bg)
+        ocoded = O.encode(ocbs, bg, p['Zc'], p['iLS'])
+        for prec, dt in (('fp64', np.float64), ('fp32', np.float32)):
+            dec = LdpcDecoder(bg, mod, 1, nref, precision=prec)
+            h1, h2, obuf = Harq(0), Harq(0), None
+            for rv in (0, 3, 2, 3):
+                rm = enc.rateMatch(coded, g, True, rv)
+                assert np.array_equal(rm, O.rate_match(ocoded, bg, zc, K, F, g, qm, 1, nref, rv)), (A, nref, rv)
+                llr = nr_link.qam_awgn_llr(rm.astype(np.int8), qm, -1.0, rng, np.float32)
+                h1.rv = h2.rv = rv
+                want_rr, obuf64, _ = O.rate_recover(llr, A, bg, qm, 1, nref, rv, None if h1.decBuffer is None else h1.decBuffer)
+                got_rr = dec.recoverRate(llr.astype(np.float64), A, h1)
+                assert np.array_equal(got_rr, want_rr) and np.array_equal(h1.decBuffer, obuf64), (A, nref, rv)
+                # fused chain without history (closed-form row skipping) and with the soft buffer
+                out, cbok, tbok = dec.decodeLLRs(llr if prec == 'fp32' else llr.astype(np.float64), A, 6,
+                                                 harq=Harq(rv))
+                otb, ocb, otbok, _, _ = rx_chain_lbrm(llr, A, bg, qm, 6, nref, rv, None, dt)
+                assert np.array_equal(out, otb[:A]) and list(cbok) == list(ocb) and bool(tbok) == otbok, (A, nref, rv, prec)
+                # device-resident batch codec: the fused load WITHOUT a soft buffer (closed-form row skipping)
+                codec = TbBatchCodec(bg, mod, A, g, 1, nref, rv, prec)
+                x = torch.from_numpy(np.stack([llr, llr])).cuda()
+                res = codec.decode(x if prec == 'fp32' else x.double(), 6)
+                torch.cuda.synchronize()
+                assert np.array_equal(res['tb'][1, :A].cpu().numpy(), otb[:A]) and bool(res['tbOk'][1].item()) == otbok
+                out, cbok, tbok = dec.decodeLLRs(llr if prec == 'fp32' else llr.astype(np.float64), A, 6, harq=h2)
+                otb, ocb, otbok, obuf, _ = rx_chain_lbrm(llr, A, bg, qm, 6, nref, rv, obuf, dt)
+                assert np.array_equal(out, otb[:A]) and bool(tbok) == otbok, (A, nref, rv, prec)
+                assert np.array_equal(h2.decBuffer, obuf.astype(np.float64)), (A, nref, rv, prec)
+
+
 def test_rate_match_repetition_and_lbrm():
     """rateMatch with E > Ncb - F (the circular buffer is sent more than once), LBRM buffers and every rv, C == 1 and
     C > 1: the staged scatter kernel's generic path (chunks that straddle interleaver rows / repeated buffers)."""
