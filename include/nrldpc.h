@@ -75,6 +75,24 @@ int nrldpc_create(int device, nrldpc_handle** out);
 int nrldpc_destroy(nrldpc_handle* h);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * Unified-memory buffers -- HARQ state that stays on the device behind host-visible arrays.
+ * HarqCW.encBuffer / HarqCW.decBuffer (harq.py:120-121, 145-178) and the [C, N] array that recoverRate hands to decode
+ * (ldpc.py:1414-1418, harq.py:169-170) are host NumPy arrays in the reference and are passed back into the codec on the
+ * next call.  Allocated here as CUDA managed memory they are valid DEVICE pointers for every entry point of this header
+ * (the kernels update them at HBM speed, nothing crosses PCIe between calls) and at the same time ordinary host memory
+ * for whoever reads them (pages migrate on a CPU access: a lazy, hardware-coherent host mirror).
+ * ---------------------------------------------------------------------------------------------------------------- */
+/* 1 if the device supports concurrent managed access (needed for the scheme above), 0 otherwise */
+int nrldpc_managed_supported(nrldpc_handle* h);
+/* *out = managed allocation of `bytes` bytes, populated on the device; zero != 0 clears it (asynchronously on `stream`) */
+int nrldpc_managed_alloc(nrldpc_handle* h, uint64_t bytes, int zero, void** out, nrldpc_stream stream);
+int nrldpc_managed_free(nrldpc_handle* h, void* p);
+/* clear a managed block on the device (asynchronously on `stream`) */
+int nrldpc_managed_clear(nrldpc_handle* h, void* p, uint64_t bytes, nrldpc_stream stream);
+/* migrate the pages to the device (to_device != 0) or to the host ahead of use; purely a performance hint */
+int nrldpc_managed_prefetch(nrldpc_handle* h, void* p, uint64_t bytes, int to_device, nrldpc_stream stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * CRC -- ChanCodeBase.getCrc / checkCrc / appendCrc, chancodebase.py:83-128, 132-157, 161-189
  * bits: [num_streams, len] int8 with row pitch `stride` (elements).  MSB-first long division, zero initial state.
  * ---------------------------------------------------------------------------------------------------------------- */

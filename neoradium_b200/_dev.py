@@ -1,10 +1,11 @@
 """Buffer plumbing between caller-owned NumPy arrays and device memory (PyTorch is only the buffer carrier)."""
 import ctypes
+import os
 
 import numpy as np
 import torch
 
-from . import _native
+from . import _managed, _native
 
 
 def device():
@@ -38,6 +39,30 @@ def to_dev(arr, dtype=None):
 
 def ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+# ---- unified-memory arrays (HARQ state resident on the device behind host-visible ndarrays, _managed.py) --------------
+def managed_ok():
+    """True when the drop-in classes may hand out ManagedArray results (env NRLDPC_NO_MANAGED=1 turns them off)."""
+    return (not os.environ.get("NRLDPC_NO_MANAGED")) and _managed.supported(device().index)
+
+
+def managed_out(shape, np_dtype, zero=False):
+    return _managed.alloc(shape, np_dtype, device().index, stream_ptr(), zero)
+
+
+def dev_in(arr, torch_dtype, np_dtype):
+    """Device view of an input array: the array itself when it is a whole ManagedArray of the right dtype (the kernels
+    read its pages in place, nothing is copied), otherwise a fresh device tensor (H2D copy + conversion)."""
+    m = _managed.root_of(arr, np_dtype)
+    if m is not None and m._nr_dev == device().index:
+        return m
+    return to_dev(arr, torch_dtype)
+
+
+def sync():
+    """Results in managed memory are read by the host right after the call returns: wait for the kernels."""
+    torch.cuda.current_stream().synchronize()
 
 
 def to_host(t):

@@ -111,6 +111,11 @@ SIGNATURES = {
     "nrldpc_graph_info": (_i32, [_i32, _vp, _vp, _vp, _vp]),
     "nrldpc_create": (_i32, [_i32, ctypes.POINTER(_vp)]),
     "nrldpc_destroy": (_i32, [_vp]),
+    "nrldpc_managed_supported": (_i32, [_vp]),
+    "nrldpc_managed_alloc": (_i32, [_vp, ctypes.c_uint64, _i32, ctypes.POINTER(_vp), _vp]),
+    "nrldpc_managed_free": (_i32, [_vp, _vp]),
+    "nrldpc_managed_clear": (_i32, [_vp, _vp, ctypes.c_uint64, _vp]),
+    "nrldpc_managed_prefetch": (_i32, [_vp, _vp, ctypes.c_uint64, _i32, _vp]),
     "nrldpc_crc": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp, _vp]),
     "nrldpc_crc_attach": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),
     "nrldpc_crc_check": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp, _vp]),

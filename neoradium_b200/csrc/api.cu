@@ -159,3 +159,55 @@ int nr_reserve_tmp(nrldpc_handle* h, size_t bytes, void** out)
     *out = h->tmp;
     return NRLDPC_OK;
 }
+
+// ---- unified-memory buffers (include/nrldpc.h, "Unified-memory buffers") ----------------------------------------------
+extern "C" int nrldpc_managed_supported(nrldpc_handle* h)
+{
+    if (!h) return 0;
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrConcurrentManagedAccess, h->device) != cudaSuccess) return 0;
+    return v ? 1 : 0;
+}
+
+extern "C" int nrldpc_managed_alloc(nrldpc_handle* h, uint64_t bytes, int zero, void** out, nrldpc_stream stream)
+{
+    if (!h || !out || bytes == 0) { nr_set_error("managed_alloc: bad argument"); return NRLDPC_ERR_ARG; }
+    *out = nullptr;
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    void* p = nullptr;
+    NR_CUDA_CHECK(cudaMallocManaged(&p, (size_t)bytes, cudaMemAttachGlobal));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemPrefetchAsync(p, (size_t)bytes, h->device, s);   // first touch on the device: no page faults in the kernels
+    if (e == cudaSuccess && zero) e = cudaMemsetAsync(p, 0, (size_t)bytes, s);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        nr_set_error("managed_alloc: %s", cudaGetErrorString(e));
+        return NRLDPC_ERR_CUDA;
+    }
+    *out = p;
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_managed_free(nrldpc_handle* h, void* p)
+{
+    if (!p) return NRLDPC_OK;
+    if (h) cudaSetDevice(h->device);
+    NR_CUDA_CHECK(cudaFree(p));
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_managed_prefetch(nrldpc_handle* h, void* p, uint64_t bytes, int to_device, nrldpc_stream stream)
+{
+    if (!h || !p) { nr_set_error("managed_prefetch: bad argument"); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    NR_CUDA_CHECK(cudaMemPrefetchAsync(p, (size_t)bytes, to_device ? h->device : cudaCpuDeviceId, (cudaStream_t)stream));
+    return NRLDPC_OK;
+}
+
+extern "C" int nrldpc_managed_clear(nrldpc_handle* h, void* p, uint64_t bytes, nrldpc_stream stream)
+{
+    if (!h || !p) { nr_set_error("managed_clear: bad argument"); return NRLDPC_ERR_ARG; }
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    NR_CUDA_CHECK(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+    return NRLDPC_OK;
+}

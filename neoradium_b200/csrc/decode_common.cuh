@@ -300,8 +300,23 @@ __device__ __forceinline__ float sub_sel(float rv, float x1, float x2, uint32_t 
 //   two-min update with the strict first-minimum record: p = |t| < min1;  p: min2 = min1 (exact FMUL by an opaque 1.0f),
 //   record (t, off);  !p: min2 = min(min2, |t|);  min1 = min(min1, |t|).  Equal to min2 = min(min2, max(min1, |t|)) because
 //   min1 <= min2 always.
+#ifndef NR_DEC_PRED_MIN1
+#define NR_DEC_PRED_MIN1 0   // 1: the running minimum too is a predicated FMUL (FMA pipe) instead of an FMNMX (ALU pipe)
+#endif
 __device__ __forceinline__ void twomin_update(uint32_t sa, float t, uint32_t off, float& min1, float& min2, float onef)
 {
+#if NR_DEC_PRED_MIN1
+    asm volatile(
+        "{.reg .pred p; .reg .f32 a;\n"
+        "abs.f32 a, %2;\n"
+        "setp.lt.f32 p, a, %0;\n"
+        "@p st.shared.v2.b32 [%3], {%4, %5};\n"
+        "@p mul.rn.f32 %1, %0, %6;\n"
+        "@!p min.f32 %1, %1, a;\n"
+        "@p mul.rn.f32 %0, a, %6;}"
+        : "+f"(min1), "+f"(min2) : "f"(t), "r"(sa), "r"(__float_as_uint(t)), "r"(off), "f"(onef));
+    return;
+#endif
     asm volatile(
         "{.reg .pred p; .reg .f32 a;\n"
         "abs.f32 a, %2;\n"

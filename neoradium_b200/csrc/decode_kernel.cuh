@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             } else {
                 load_cols(float());
             }
-            for (int row = 0; row < (SBG != 0 ? 0 : 4); row++) {   // static kernels: the first iteration never reads it
+            for (int row = 0; row < ((SBG != 0 && NR_DEC_FIRST_SPECIAL) ? 0 : 4); row++) {   // static kernels: the first iteration never reads it
                 RowState<T> st0;
                 st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = (T)0;
                 store.store(row, st0);
@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             if constexpr (SBG != 0) {
                 uint32_t* pe = (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr;
                 RowCtx2<SBG, 0> c0;
-                if (it == 0) {   // all messages are +0: t = r, no state to read (decode_static.cuh)
+                if (NR_DEC_FIRST_SPECIAL && it == 0) {   // all messages are +0: t = r, no state to read (decode_static.cuh)
                     prep_row2<SBG, 0, ZS, true>(g, mB, L2, store, dummyOff2, c0);
                     run_rows_static2<SBG, 0, (ESM != 0), ZS, true>(g, a.numRows, rbS, mB, L2, store, slot, dummyOff2, lb, c0, pe);
                 } else {

@@ -75,6 +75,9 @@ struct EdgeTab<BG, 0> {
     static __device__ __forceinline__ uint32_t kz(const Lift2& L) { return L.kz; }
 };
 
+#ifndef NR_DEC_FIRST_SPECIAL
+#define NR_DEC_FIRST_SPECIAL 1   // separate instantiation of the first iteration (no old messages); 0 = one code path
+#endif
 __device__ __forceinline__ uint32_t tagged_offset(uint32_t mB, uint32_t one, uint32_t x, uint32_t negZB)
 {
     uint32_t w;

@@ -169,32 +169,45 @@ class LdpcEncoder(LdpcBase):
         self.numFillerBits = self.codeBlockSize - bitsPerCodeBlock - (24 if c > 1 else 0)
         cfg, _, _ = self._tb_config()
         d = _dev.to_dev(txBlock, torch.int8).reshape(1, -1)
-        out = torch.empty((c, self.codeBlockSize), dtype=torch.int8, device=d.device)
+        # dtype: int8 when C > 1 (ldpc.py:1020), otherwise the input's dtype promoted with int8 (ldpc.py:1016)
+        rdt = np.dtype(np.int8) if c > 1 else np.result_type(txBlock.dtype, np.int8)
+        managed = rdt == np.int8 and _dev.managed_ok()      # stays on the device for encode() (see _managed.py)
+        out = (_dev.managed_out((c, self.codeBlockSize), np.int8) if managed
+               else torch.empty((c, self.codeBlockSize), dtype=torch.int8, device=d.device))
         _native.check(_native.lib().nrldpc_segment(_dev.handle(), cfg, _dev.ptr(d), 1, len(txBlock), len(txBlock),
                                                    _dev.ptr(out), _dev.stream_ptr()))
-        res = _dev.to_host(out)
-        # dtype: int8 when C > 1 (ldpc.py:1020), otherwise the input's dtype promoted with int8 (ldpc.py:1016)
-        return res if c > 1 else res.astype(np.result_type(txBlock.dtype, np.int8))
+        if managed:
+            _dev.sync()
+            return out
+        return _dev.to_host(out).astype(rdt)
 
     # ------------------------------------------------------------------------------------------------------------------
     def encode(self, codeBlocks, puncture=True):
         """C x K code blocks -> C x N encoded blocks (ldpc.py:1033-1090)."""
-        codeBlocks = np.asarray(codeBlocks)
+        codeBlocks = np.asanyarray(codeBlocks)      # (keeps a ManagedArray: its pages are read on the device in place)
         z = self.liftingSize
         P, n2, k = params.bg_dims(self.baseGraphNo)
         c, kk = codeBlocks.shape
         assert kk == k * z
-        d = _dev.to_dev(codeBlocks, torch.int8)
+        d = _dev.dev_in(codeBlocks, torch.int8, np.int8)
         cols = n2 - 2 if puncture else n2
-        out = torch.empty((c, cols * z), dtype=torch.int8, device=d.device)
+        rdt = np.result_type(codeBlocks.dtype, np.int8)
+        # the encoded blocks are HarqCW.encBuffer (harq.py:160): a ManagedArray keeps them on the device for the
+        # rateMatch calls of every (re)transmission
+        managed = rdt == np.int8 and _dev.managed_ok()
+        out = (_dev.managed_out((c, cols * z), np.int8) if managed
+               else torch.empty((c, cols * z), dtype=torch.int8, device=d.device))
         _native.check(_native.lib().nrldpc_encode(_dev.handle(), self.baseGraphNo, z, _dev.ptr(d), c, _dev.ptr(out),
                                                   1 if puncture else 0, _dev.stream_ptr()))
-        return _dev.to_host(out).astype(np.result_type(codeBlocks.dtype, np.int8))
+        if managed:
+            _dev.sync()
+            return out
+        return _dev.to_host(out).astype(rdt)
 
     # ------------------------------------------------------------------------------------------------------------------
     def rateMatch(self, codedBlocks, g=None, concatCBs=True, rv=0):
         """C x N encoded blocks -> rate-matched, interleaved bits (ldpc.py:1093-1159)."""
-        codedBlocks = np.asarray(codedBlocks)
+        codedBlocks = np.asanyarray(codedBlocks)      # (keeps a ManagedArray: its pages are read on the device in place)
         c, nz = codedBlocks.shape
         z = self.liftingSize
         assert nz in [66 * z, 50 * z]
@@ -206,7 +219,7 @@ class LdpcEncoder(LdpcBase):
         cfg.C = c
         lens = params.rate_matched_cb_lens(g, c, self.txLayers, self.qm)
         total = int(sum(lens))
-        d = _dev.to_dev(codedBlocks, torch.int8)
+        d = _dev.dev_in(codedBlocks, torch.int8, np.int8)
         out = torch.empty((total,), dtype=torch.int8, device=d.device)
         _native.check(_native.lib().nrldpc_rate_match(_dev.handle(), cfg, _dev.ptr(d), 1, _dev.ptr(out), total,
                                                       _dev.stream_ptr()))
@@ -330,51 +343,74 @@ class LdpcDecoder(LdpcBase):
                 f"HARQ buffer shape mismatch! It must be a {c}x{cirBufSize} NumPy array!"
         x = _dev.to_dev(rxBlock, torch.float64).reshape(-1)
         need_buf = harq is not None
+        managed = _dev.managed_ok()
+        # HARQ soft buffer (HarqCW.decBuffer, harq.py:121): a ManagedArray created here stays on the device between the
+        # transmissions of a transport block; a caller-supplied plain array is combined and updated IN PLACE like the
+        # reference does (ldpc.py:1410), which costs one upload and one download
+        mbuf = None
         if need_buf:
-            buf = (torch.zeros((c, cirBufSize), dtype=torch.float64, device=x.device) if hostBuf is None
-                   else _dev.to_dev(hostBuf, torch.float64))
+            if hostBuf is None and managed:
+                mbuf = buf = _dev.managed_out((c, cirBufSize), np.float64, zero=True)
+            elif hostBuf is not None and managed and _dev.dev_in(hostBuf, torch.float64, np.float64) is hostBuf:
+                mbuf = buf = hostBuf
+            else:
+                buf = (torch.zeros((c, cirBufSize), dtype=torch.float64, device=x.device) if hostBuf is None
+                       else _dev.to_dev(hostBuf, torch.float64))
         else:
             buf = None
-        out = torch.empty((c, ncb), dtype=torch.float64, device=x.device)
+        out = (_dev.managed_out((c, ncb), np.float64) if managed
+               else torch.empty((c, ncb), dtype=torch.float64, device=x.device))
         _native.check(_native.lib().nrldpc_rate_recover(_dev.handle(), cfg, _native.F64, _dev.ptr(x), 1, x.numel(),
                                                         x.numel(), _dev.ptr(buf), _dev.ptr(out), _dev.stream_ptr()))
         if need_buf:
-            newBuf = _dev.to_host(buf)
-            if hostBuf is not None and isinstance(hostBuf, np.ndarray) and hostBuf.dtype == np.float64:
-                hostBuf[...] = newBuf           # the reference mutates the caller's array in place (ldpc.py:1410)
-                harq.decBuffer = hostBuf
+            if mbuf is not None:
+                harq.decBuffer = mbuf
             else:
-                harq.decBuffer = newBuf
+                newBuf = _dev.to_host(buf)
+                if hostBuf is not None and isinstance(hostBuf, np.ndarray) and hostBuf.dtype == np.float64:
+                    hostBuf[...] = newBuf           # the reference mutates the caller's array in place (ldpc.py:1410)
+                    harq.decBuffer = hostBuf
+                else:
+                    harq.decBuffer = newBuf
+        if managed:
+            _dev.sync()
+            return out
         return _dev.to_host(out)
 
     # ------------------------------------------------------------------------------------------------------------------
     def decode(self, rxCodeBlock, numIter=5, onlyInfoBits=True, outputBelief=False):
         """Layered normalised min-sum decoding of C x N LLRs (ldpc.py:1495-1581)."""
-        rxCodeBlock = np.asarray(rxCodeBlock)
+        rxCodeBlock = np.asanyarray(rxCodeBlock)      # (keeps a ManagedArray: its pages are read on the device in place)
         c, nIn = rxCodeBlock.shape
         z = self.liftingSize
         P, n, k = params.bg_dims(self.baseGraphNo)
         assert nIn % z == 0 and nIn // z + 2 == n
         in64 = rxCodeBlock.dtype != np.float32
-        x = _dev.to_dev(rxCodeBlock if rxCodeBlock.dtype in (np.float32, np.float64)
-                        else rxCodeBlock.astype(np.float64))
+        if rxCodeBlock.dtype in (np.float32, np.float64):     # (a ManagedArray from recoverRate is read in place)
+            x = _dev.dev_in(rxCodeBlock, torch.float64 if in64 else torch.float32, rxCodeBlock.dtype)
+        else:
+            x = _dev.to_dev(rxCodeBlock.astype(np.float64))
         outCols = k if onlyInfoBits else n
         tdt = _TORCH_F[self.precision]
+        managed = _dev.managed_ok()
         bits = beliefs = None
         if outputBelief:
-            beliefs = torch.empty((c, outCols * z), dtype=tdt, device=x.device)
+            beliefs = (_dev.managed_out((c, outCols * z), np.float64) if managed and self.precision == 'fp64'
+                       else torch.empty((c, outCols * z), dtype=tdt, device=x.device))
         else:
-            bits = torch.empty((c, outCols * z), dtype=torch.int8, device=x.device)
+            bits = (_dev.managed_out((c, outCols * z), np.int8) if managed
+                    else torch.empty((c, outCols * z), dtype=torch.int8, device=x.device))
         iters = torch.empty((c,), dtype=torch.int32, device=x.device)
         flags = _native.dec_flags(self.earlyStop, self.earlyStopFrom)
         _native.check(_native.lib().nrldpc_decode(
             _dev.handle(), self.baseGraphNo, z, _native.F64 if in64 else _native.F32, _NATIVE_F[self.precision],
             _dev.ptr(x), c, nIn, n - 2, int(numIter), flags, outCols, _dev.ptr(bits), _dev.ptr(beliefs),
             _dev.ptr(iters), _dev.stream_ptr()))
-        self.lastIterations = _dev.to_host(iters)
-        if outputBelief:
-            return _dev.to_host(beliefs).astype(np.float64)
-        return _dev.to_host(bits)
+        self.lastIterations = _dev.to_host(iters)      # (synchronises the stream: managed results are complete)
+        res = beliefs if outputBelief else bits
+        if isinstance(res, np.ndarray):
+            return res
+        return _dev.to_host(res).astype(np.float64) if outputBelief else _dev.to_host(res)
 
     # ------------------------------------------------------------------------------------------------------------------
     def decode2(self, rxCodeBlock, maxIter=6, onlyInfoBits=True, outputBelief=False, alpha=0.75, stopOnGoodParity=True):
@@ -383,7 +419,7 @@ class LdpcDecoder(LdpcBase):
         ``stopOnGoodParity`` stops a block after the first iteration whose hard decisions satisfy EVERY parity check; the
         reference's own test looks at the first base-graph row only (``isValidCodedBlock``, ldpc.py:841-843), so with
         ``stopOnGoodParity=True`` it may stop earlier than this one.  ``lastIterations`` holds the per-block counts."""
-        rxCodeBlock = np.asarray(rxCodeBlock)
+        rxCodeBlock = np.asanyarray(rxCodeBlock)      # (keeps a ManagedArray: its pages are read on the device in place)
         c, nIn = rxCodeBlock.shape
         z = self.liftingSize
         P, n, k = params.bg_dims(self.baseGraphNo)
@@ -410,11 +446,11 @@ class LdpcDecoder(LdpcBase):
     # ------------------------------------------------------------------------------------------------------------------
     def checkCrcAndMerge(self, rxCodedBlocks):
         """CRC check of every decoded code block and re-assembly of the transport block (ldpc.py:1584-1619)."""
-        rxCodedBlocks = np.asarray(rxCodedBlocks)
+        rxCodedBlocks = np.asanyarray(rxCodedBlocks)      # (keeps a ManagedArray: its pages are read on the device in place)
         c = self.numCodeBlocks
         cfg, _, _ = self._tb_config()
-        d = _dev.to_dev(rxCodedBlocks, torch.int8)
-        assert d.shape == (c, self.codeBlockSize)
+        d = _dev.dev_in(rxCodedBlocks, torch.int8, np.int8)
+        assert tuple(d.shape) == (c, self.codeBlockSize)
         per = self.codeBlockSize - self.numFillerBits - (24 if c > 1 else 0)
         tb = torch.empty((c * per,), dtype=torch.int8, device=d.device)
         ok = torch.empty((c,), dtype=torch.uint8, device=d.device)

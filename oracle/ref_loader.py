@@ -1,7 +1,9 @@
 """Loader for the UNMODIFIED reference (InterDigitalInc/NeoRadium v0.4.0) -- container-only test infrastructure.
 
-The reference is pure Python and lives read-only under /root/reference.  It does not exist on the GPU box, so
-nothing that runs there (gpu tests, smoke(), bench.py) may import this module; it is used by
+The reference is pure Python and lives read-only under /root/reference.  That path does not exist on the GPU box; the
+only thing there is the optional, unmodified pip-installed copy under baseline/_ref (git-ignored), which the
+"real callers" check (tests/test_gpu_real_callers.py, scripts/run_harq_notebook.py) and bench.py's reference arm use when
+it is present.  Otherwise this module is used by
   * oracle/gen_tables.py   (emits the 3GPP shift tables in this repo's own formats)
   * oracle/gen_golden.py   (emits tests/golden/*.npz fixtures)
   * tests marked `needs_reference` (skipped automatically when /root/reference is absent)
@@ -15,7 +17,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("NEORADIUM_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference (this container) or, on the GPU box, the unmodified copy that
+    `pip install --no-deps --target baseline/_ref /root/reference` left under the repository (git-ignored)."""
+    cands = [os.environ.get("NEORADIUM_REFERENCE"), "/root/reference", os.path.join(_HERE, "..", "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "neoradium", "ldpc.py")):
+            return os.path.abspath(c)
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available():
