@@ -73,6 +73,36 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, ok, tb
 
 
+def _cpu_worker_ref(args):
+    """The same chain through the UNMODIFIED reference (neoradium/ldpc.py: recoverRate -> decode(numIter=8) ->
+    checkCrcAndMerge -> checkCrc('24A'), harq.py:165-173), imported from the pip-installed copy under baseline/_ref."""
+    llr, reps = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import ref_loader
+    ldpc = ref_loader.load_reference("ldpc")
+    dec = ldpc.LdpcDecoder(BG, MOD, 1, 0)
+    t0 = time.perf_counter()
+    ok = True
+    for _ in range(reps):
+        rr = dec.recoverRate(llr.astype(np.float64), A)
+        tb, crc = dec.checkCrcAndMerge(dec.decode(rr, numIter=NUM_ITER))
+        ok = ok and bool(dec.checkCrc(tb, '24A')) and bool(np.all(crc))
+    return time.perf_counter() - t0, ok, tb[:-24]
+
+
+def _reference_worker():
+    """(worker, kind): the unmodified reference when a copy travels with the repository (baseline/_ref), else the oracle port"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_loader
+        if ref_loader.reference_available():
+            return _cpu_worker_ref, "reference", ref_loader.REFERENCE_ROOT
+    except Exception:
+        pass
+    return _cpu_worker, "port", None
+
+
 def _cpu_worker_c(args):
     """The same chain with the compiled scalar C restatement (oracle/nr_oracle_c.c: float64 decode of all 46 rows,
     bit-serial CRC) -- a secondary, friendlier CPU figure than the reference's NumPy code."""
@@ -122,13 +152,14 @@ def run_reference(args):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     llr, _ = _cpu_make_llr(SEED)
+    worker, kind, ref_root = _reference_worker()
     pool = mp.get_context("fork").Pool(cores)
     jobs = [(llr, 1)] * cores
     for _ in range(max(0, min(args.warmup, 1))):      # one warm-up pass is enough for a CPU loop
-        pool.map(_cpu_worker, jobs)
+        pool.map(worker, jobs)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        pool.map(_cpu_worker, jobs)
+        pool.map(worker, jobs)
     wall = time.perf_counter() - t0
     pool.close()
     bits = args.steps * cores * A
@@ -137,10 +168,11 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus, 64),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": "each step: %d transport blocks (C=16, %d code blocks) of the workload, one per host "
-                                       "core, through the NumPy oracle port of recoverRate->decode(8)->checkCrcAndMerge->"
-                                       "checkCrc (float64, the reference's arithmetic)" % (cores, cores * C_PER_TB)},
+                                       "core, through %s recoverRate->decode(8)->checkCrcAndMerge->checkCrc (float64)"
+                                       % (cores, cores * C_PER_TB, "the UNMODIFIED reference (neoradium/ldpc.py from %s):" % ref_root
+                                          if kind == "reference" else "the NumPy oracle port of")},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -454,12 +486,14 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         sample = [llrs[0][i].cpu().numpy() for i in range(min(tbs, cores))]
-        gbps, wall, res_cpu = cpu_baseline(sample, cores)
+        worker, kind, ref_root = _reference_worker()
+        gbps, wall, res_cpu = cpu_baseline(sample, cores, worker=worker)
         same = all(np.array_equal(res_cpu[i][2], out_tb) for i, out_tb in
                    enumerate(codec.decode(llrs[0], NUM_ITER)["tb"][:min(tbs, cores), :A].cpu().numpy()))
-        cpu = {"value": gbps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d transport blocks (%d code blocks) of the timed batch, one per host core, NumPy oracle port "
-                         "of the reference algorithm in float64, %.1f s wall" % (cores, cores * C_PER_TB, wall),
+        cpu = {"value": gbps, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "%d transport blocks (%d code blocks) of the timed batch, one per host core, %s in float64, %.1f s wall"
+                         % (cores, cores * C_PER_TB, ("the unmodified reference (neoradium/ldpc.py, %s)" % ref_root) if kind == "reference"
+                            else "NumPy oracle port of the reference algorithm", wall),
                "bits_identical_to_gpu": bool(same)}
         gbps_c, wall_c, res_c = cpu_baseline(sample, cores, reps=4, worker=_cpu_worker_c)
         cpu["c_port"] = {"value": gbps_c, "unit": UNIT, "cores": cores,

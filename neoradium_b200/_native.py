@@ -102,6 +102,14 @@ class TbConfig(ctypes.Structure):
 
 _cfgp = ctypes.POINTER(TbConfig)
 
+
+class TbGroup(ctypes.Structure):
+    """struct nrldpc_tb_group"""
+    _fields_ = [("cfg", TbConfig), ("in_dtype", ctypes.c_int32), ("reserved", ctypes.c_int32), ("llr", ctypes.c_void_p),
+                ("num_tb", ctypes.c_int64), ("llr_len", ctypes.c_int64), ("llr_stride", ctypes.c_int64),
+                ("soft_buffer", ctypes.c_void_p), ("tb_bits", ctypes.c_void_p), ("tb_bits_stride", ctypes.c_int64),
+                ("cb_crc_ok", ctypes.c_void_p), ("tb_crc_ok", ctypes.c_void_p), ("iters", ctypes.c_void_p)]
+
 # every symbol include/nrldpc.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "nrldpc_version": (_i32, []),
@@ -123,6 +131,7 @@ SIGNATURES = {
     "nrldpc_encode": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     "nrldpc_rate_match": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp]),
     "nrldpc_parity_check": (_i32, [_vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "nrldpc_parity_check_rows": (_i32, [_vp, _i32, _i32, _vp, _i64, _i32, _vp, _vp]),
     "nrldpc_rate_recover": (_i32, [_vp, _cfgp, _i32, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "nrldpc_decode": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, _i32, _i32, _vp, _vp, _vp,
                              _vp]),
@@ -130,6 +139,7 @@ SIGNATURES = {
                               _vp, _vp, _vp]),
     "nrldpc_decode_tb": (_i32, [_vp, _cfgp, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp,
                                 _vp, _vp, _vp]),
+    "nrldpc_decode_tb_groups": (_i32, [_vp, ctypes.POINTER(TbGroup), _i32, _i32, _i32, _i32, _vp]),
     "nrldpc_check_crc_and_merge": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nrldpc_accumulate_counters": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "nrldpc_modulate": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),

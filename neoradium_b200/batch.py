@@ -61,7 +61,18 @@ class TbBatchCodec:
         self.cfg = _native.TbConfig(bg=self.bg, zc=self.Zc, K=self.K, F=self.F, C=self.C, qm=self.qm, nl=self.nl,
                                     ncb=self.ncb, rv=self.rv, reserved=0, G=self.G)
         devIdx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._ownHandle = bool(ownHandle)
         self._h = _native.new_handle(devIdx) if ownHandle else _native.handle(devIdx)
+
+    def __del__(self):
+        # a private handle dies with its codec (after the device has drained: its scratch may still be in use)
+        try:
+            if getattr(self, '_ownHandle', False) and self._h is not None:
+                torch.cuda.synchronize(self.device)
+                _native.lib().nrldpc_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------------------------------------------------------
     def encode(self, payload):
@@ -131,8 +142,10 @@ class TbBatchCodec:
             self._streams = tuple(torch.cuda.Stream(self.device) for _ in range(3))
             self._pipe = {}
         st = self._pipe.get(slot)
+        if st is not None and st['key'] != key and st.get('done') is not None:
+            st['done'].synchronize()          # the old staging buffers are about to be freed: let their last use finish
         if st is None or st['key'] != key:
-            st = dict(key=key, h2d=self._streams[0], comp=self._streams[1], d2h=self._streams[2],
+            st = dict(key=key, done=None, h2d=self._streams[0], comp=self._streams[1], d2h=self._streams[2],
                       din=[torch.empty((bounds[i + 1] - bounds[i], Gp), dtype=x.dtype, device=self.device)
                            for i in range(chunks)],
                       dout=[self.alloc_outputs(bounds[i + 1] - bounds[i]) for i in range(chunks)])
@@ -146,6 +159,8 @@ class TbBatchCodec:
         cur = torch.cuda.current_stream(self.device)
         for s_ in (st['h2d'], st['comp'], st['d2h']):
             s_.wait_stream(cur)
+        if st['done'] is not None:
+            st['h2d'].wait_event(st['done'])  # this slot's previous call still owns din / dout until its last D2H copy
         for i in range(chunks):
             lo, hi = bounds[i], bounds[i + 1]
             with torch.cuda.stream(st['h2d']):
@@ -161,10 +176,11 @@ class TbBatchCodec:
                 st['d2h'].wait_event(ev_done)
                 for k in ('tb', 'cbOk', 'tbOk', 'iters'):
                     hout[k][lo:hi].copy_(st['dout'][i][k], non_blocking=True)
+        with torch.cuda.stream(st['d2h']):
+            done = torch.cuda.Event()
+            done.record()
+        st['done'] = done
         if not wait:
-            with torch.cuda.stream(st['d2h']):
-                done = torch.cuda.Event()
-                done.record()
             return PendingDecode(hout, done)
         st['d2h'].synchronize()
         return hout
@@ -185,6 +201,38 @@ class TbBatchCodec:
             _dev.ptr(out['tb']) if ref is not None else None, _dev.ptr(ref), self.A, self.C * self.per,
             _dev.ptr(counters), _dev.stream_ptr()))
         return counters
+
+
+def decode_groups(codecs, llrs, numIter, outs=None, softBuffers=None):
+    """Mixed-configuration batch in ONE library call (BASELINE configs[2]: the codewords of a PDSCH slot differ in base
+    graph, lifting size, layers, redundancy version; harq.py:331-347 loops over them on the host).  ``codecs[i]`` describes
+    group i (a ``TbBatchCodec``: its equally configured transport blocks), ``llrs[i]`` is its [numTb_i, G_i] device tensor,
+    ``softBuffers[i]`` its device-resident HARQ buffer or None.  The descriptor array goes to ``nrldpc_decode_tb_groups``,
+    which runs the groups concurrently on the library's internal streams (forked from / joined into the current stream).
+    All codecs must share precision and early-termination settings.  Returns the list of output dicts."""
+    n = len(codecs)
+    assert n == len(llrs) and n > 0
+    c0 = codecs[0]
+    assert all(c.precision == c0.precision and c.earlyStop == c0.earlyStop and c.earlyStopFrom == c0.earlyStopFrom
+               for c in codecs), "one call, one precision / early-termination setting"
+    if outs is None:
+        outs = [c.alloc_outputs(x.shape[0]) for c, x in zip(codecs, llrs)]
+    if softBuffers is None:
+        softBuffers = [None] * n
+    arr = (_native.TbGroup * n)()
+    for i, (c, x, o, sb) in enumerate(zip(codecs, llrs, outs, softBuffers)):
+        g = arr[i]
+        g.cfg = c.cfg
+        g.in_dtype = _IN_DTYPE[x.dtype]
+        g.llr = x.data_ptr()
+        g.num_tb, g.llr_len, g.llr_stride = x.shape[0], x.shape[1], x.stride(0)
+        g.soft_buffer = sb.data_ptr() if sb is not None else None
+        g.tb_bits, g.tb_bits_stride = o['tb'].data_ptr(), c.C * c.per
+        g.cb_crc_ok, g.tb_crc_ok, g.iters = o['cbOk'].data_ptr(), o['tbOk'].data_ptr(), o['iters'].data_ptr()
+    _native.check(_native.lib().nrldpc_decode_tb_groups(
+        c0._h, arr, n, _native.F64 if c0.precision == 'fp64' else _native.F32, int(numIter),
+        _native.dec_flags(c0.earlyStop, c0.earlyStopFrom), _dev.stream_ptr()))
+    return outs
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -126,6 +126,12 @@ extern "C" int nrldpc_destroy(nrldpc_handle* h)
     if (h->tmp) cudaFree(h->tmp);
     if (h->tmp2) cudaFree(h->tmp2);
     if (h->goldTables) cudaFree(h->goldTables);
+    for (int i = 0; i < 4; i++) {
+        if (h->sub[i]) nrldpc_destroy(h->sub[i]);
+        if (h->subStream[i]) cudaStreamDestroy(h->subStream[i]);
+        if (h->subJoin[i]) cudaEventDestroy(h->subJoin[i]);
+    }
+    if (h->subFork) cudaEventDestroy(h->subFork);
     if (h->crcFacDev) cudaFree(h->crcFacDev);
     if (h->tbAcc) cudaFree(h->tbAcc);
     if (h->tbFacDev) cudaFree(h->tbFacDev);

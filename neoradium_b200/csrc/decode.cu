@@ -319,6 +319,7 @@ extern "C" int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, in
     a.numRows = g.P;          // every row: the closed form of skipped rows is specific to the standard rule
     a.trueMin2 = 1;
     a.alpha = alpha;
+    a.synRows = (stop_on_good_parity == 2) ? 1 : 0;   // 2: the reference's first-row-only stop test (ldpc.py:841-843, 1483-1485)
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, (cudaStream_t)stream);
 }
 
@@ -412,4 +413,36 @@ extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, i
         a.numRows = max(4, min(g.P, lastFull - g.ksys + 1));
     }
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, s);
+}
+
+extern "C" int nrldpc_decode_tb_groups(nrldpc_handle* h, const nrldpc_tb_group* groups, int num_groups, int compute_dtype,
+                                       int num_iter, int flags, nrldpc_stream stream)
+{
+    if (!h || !groups || num_groups <= 0) { nr_set_error("decode_tb_groups: bad argument"); return NRLDPC_ERR_ARG; }
+    auto run = [&](nrldpc_handle* hh, const nrldpc_tb_group& g, cudaStream_t s) {
+        return nrldpc_decode_tb(hh, &g.cfg, g.in_dtype, compute_dtype, g.llr, g.num_tb, g.llr_len, g.llr_stride, g.soft_buffer,
+                                num_iter, flags, g.tb_bits, g.tb_bits_stride, g.cb_crc_ok, g.tb_crc_ok, g.iters, (nrldpc_stream)s);
+    };
+    cudaStream_t s = (cudaStream_t)stream;
+    if (num_groups == 1) return run(h, groups[0], s);
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    const int nsub = num_groups < 4 ? num_groups : 4;
+    if (!h->subFork) NR_CUDA_CHECK(cudaEventCreateWithFlags(&h->subFork, cudaEventDisableTiming));
+    for (int i = 0; i < nsub; i++) {
+        if (!h->sub[i]) {
+            int rc = nrldpc_create(h->device, &h->sub[i]);
+            if (rc) return rc;
+            NR_CUDA_CHECK(cudaStreamCreateWithFlags(&h->subStream[i], cudaStreamNonBlocking));
+            NR_CUDA_CHECK(cudaEventCreateWithFlags(&h->subJoin[i], cudaEventDisableTiming));
+        }
+    }
+    NR_CUDA_CHECK(cudaEventRecord(h->subFork, s));
+    for (int i = 0; i < nsub; i++) NR_CUDA_CHECK(cudaStreamWaitEvent(h->subStream[i], h->subFork, 0));
+    int rc = NRLDPC_OK;
+    for (int i = 0; i < num_groups && rc == NRLDPC_OK; i++) rc = run(h->sub[i % nsub], groups[i], h->subStream[i % nsub]);
+    for (int i = 0; i < nsub; i++) {   // join even after an error: the caller's stream must not run ahead of queued work
+        cudaEventRecord(h->subJoin[i], h->subStream[i]);
+        cudaStreamWaitEvent(s, h->subJoin[i], 0);
+    }
+    return rc;
 }

@@ -73,6 +73,7 @@ struct DecArgs {
     // decode2 (ldpc.py:1421-1492): true second minimum and a caller-chosen alpha; generic kernels only
     int trueMin2;
     double alpha;
+    int synRows;        // generic kernels: rows of the early-termination syndrome (0 = all scheduled rows; 1 = decode2 compatibility)
     // static kernels with NRLDPC_DEC_EARLY_STOP: words of the bit-packed hard decisions (multiple of 4), see the kernel
     int packWords;
 };

@@ -533,7 +533,8 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 // satisfied by construction: their parity bit is the parity of the rest)
                 uint32_t bad = 0;
                 if (active && !cbDone) {
-                    for (int row = 0; row < a.numRows; row++) {
+                    const int synRows = (a.synRows > 0 && a.synRows < a.numRows) ? a.synRows : a.numRows;
+                    for (int row = 0; row < synRows; row++) {
                         const int e0 = g.rowEdge0[row];
                         const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
                         uint32_t par = 0;

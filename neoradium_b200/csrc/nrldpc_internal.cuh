@@ -41,6 +41,10 @@ struct nrldpc_handle {
     void* tbFacDev;         // cached x^(per (C-1-r)) mod g24A of the fused decoder, key below
     unsigned long long tbFacKey;
     size_t tbFacCap;
+    // nrldpc_decode_tb_groups: private sub-handles (own scratch / temporaries / work queue) on internal streams
+    nrldpc_handle* sub[4];
+    cudaStream_t subStream[4];
+    cudaEvent_t subFork, subJoin[4];
     void* goldTables;       // device copy of the Gold-sequence jump tables (linksim.cu), created on first use
     int smemPerSM;
     int decOcc;             // target resident decoder CTAs per SM (0 = automatic), env NRLDPC_DEC_OCC

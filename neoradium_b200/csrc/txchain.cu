@@ -556,12 +556,20 @@ extern "C" int nrldpc_encode(nrldpc_handle* h, int bg, int zc, const int8_t* cod
 extern "C" int nrldpc_parity_check(nrldpc_handle* h, int bg, int zc, const int8_t* coded_full, int64_t num_cb,
                                    uint8_t* ok, nrldpc_stream stream)
 {
+    return nrldpc_parity_check_rows(h, bg, zc, coded_full, num_cb, 0, ok, stream);
+}
+
+extern "C" int nrldpc_parity_check_rows(nrldpc_handle* h, int bg, int zc, const int8_t* coded_full, int64_t num_cb,
+                                        int rows, uint8_t* ok, nrldpc_stream stream)
+{
     if (!h) { nr_set_error("parity_check: null handle"); return NRLDPC_ERR_ARG; }
     NrGraph g;
     if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
-    if (num_cb <= 0) { nr_set_error("parity_check: bad shape"); return NRLDPC_ERR_ARG; }
+    if (num_cb <= 0 || rows < 0) { nr_set_error("parity_check: bad shape"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    if (zc % 16 == 0 && ((uintptr_t)coded_full & 15) == 0 && !getenv("NRLDPC_ENC_BYTEWISE")) {
+    const bool allRows = rows == 0 || rows >= g.P;
+    if (!allRows) g.P = rows;   // the first `rows` base-graph rows only (rows = 1: the reference's isValidCodedBlock, ldpc.py:841-843)
+    if (allRows && zc % 16 == 0 && ((uintptr_t)coded_full & 15) == 0 && !getenv("NRLDPC_ENC_BYTEWISE")) {
         const int W = (zc + 31) / 32, DW = (2 * zc + 31) / 32 + 2;
         const size_t smemP = (size_t)(g.ncore * DW + (g.P - 4) * W) * sizeof(uint32_t);
         const int gridP = (int)min((long long)num_cb, (long long)h->numSMs * 16);

@@ -103,16 +103,18 @@ class LdpcBase(ChanCodeBase):
     def isValidCodeword(self, codeWord):
         return self.isValidCodedBlock(codeWord)
 
-    def isValidCodedBlock(self, codedBlock):
-        """True if ``codedBlock`` (length n*Zc, un-punctured) satisfies every parity check (ldpc.py:825-843)."""
+    def isValidCodedBlock(self, codedBlock, firstRowOnly=False):
+        """True if ``codedBlock`` (length n*Zc, un-punctured) satisfies every parity check (ldpc.py:825-843).
+        ``firstRowOnly=True`` (compatibility switch) tests what the reference's loop actually tests: it returns from inside
+        the first base-graph row (ldpc.py:841-843), so only those Zc checks are looked at."""
         cb = np.asarray(codedBlock).reshape(-1)
         z = self.liftingSize
         P, n, _ = params.bg_dims(self.baseGraphNo)
         assert cb.shape[0] == n * z
         d = _dev.to_dev(cb.astype(np.int64) if cb.dtype.kind == 'f' else cb, torch.int8).reshape(1, -1)
         ok = torch.empty((1,), dtype=torch.uint8, device=d.device)
-        _native.check(_native.lib().nrldpc_parity_check(_dev.handle(), self.baseGraphNo, z, _dev.ptr(d), 1,
-                                                        _dev.ptr(ok), _dev.stream_ptr()))
+        _native.check(_native.lib().nrldpc_parity_check_rows(_dev.handle(), self.baseGraphNo, z, _dev.ptr(d), 1,
+                                                             1 if firstRowOnly else 0, _dev.ptr(ok), _dev.stream_ptr()))
         return bool(_dev.to_host(ok)[0])
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -171,7 +173,7 @@ class LdpcEncoder(LdpcBase):
         d = _dev.to_dev(txBlock, torch.int8).reshape(1, -1)
         # dtype: int8 when C > 1 (ldpc.py:1020), otherwise the input's dtype promoted with int8 (ldpc.py:1016)
         rdt = np.dtype(np.int8) if c > 1 else np.result_type(txBlock.dtype, np.int8)
-        managed = rdt == np.int8 and _dev.managed_ok()      # stays on the device for encode() (see _managed.py)
+        managed = rdt == np.int8 and _dev.managed_ok(c * self.codeBlockSize)      # stays on the device for encode() (see _managed.py)
         out = (_dev.managed_out((c, self.codeBlockSize), np.int8) if managed
                else torch.empty((c, self.codeBlockSize), dtype=torch.int8, device=d.device))
         _native.check(_native.lib().nrldpc_segment(_dev.handle(), cfg, _dev.ptr(d), 1, len(txBlock), len(txBlock),
@@ -194,7 +196,7 @@ class LdpcEncoder(LdpcBase):
         rdt = np.result_type(codeBlocks.dtype, np.int8)
         # the encoded blocks are HarqCW.encBuffer (harq.py:160): a ManagedArray keeps them on the device for the
         # rateMatch calls of every (re)transmission
-        managed = rdt == np.int8 and _dev.managed_ok()
+        managed = rdt == np.int8 and _dev.managed_ok(c * cols * z)
         out = (_dev.managed_out((c, cols * z), np.int8) if managed
                else torch.empty((c, cols * z), dtype=torch.int8, device=d.device))
         _native.check(_native.lib().nrldpc_encode(_dev.handle(), self.baseGraphNo, z, _dev.ptr(d), c, _dev.ptr(out),
@@ -343,7 +345,7 @@ class LdpcDecoder(LdpcBase):
                 f"HARQ buffer shape mismatch! It must be a {c}x{cirBufSize} NumPy array!"
         x = _dev.to_dev(rxBlock, torch.float64).reshape(-1)
         need_buf = harq is not None
-        managed = _dev.managed_ok()
+        managed = _dev.managed_ok(c * ncb * 8)
         # HARQ soft buffer (HarqCW.decBuffer, harq.py:121): a ManagedArray created here stays on the device between the
         # transmissions of a transport block; a caller-supplied plain array is combined and updated IN PLACE like the
         # reference does (ldpc.py:1410), which costs one upload and one download
@@ -392,7 +394,7 @@ class LdpcDecoder(LdpcBase):
             x = _dev.to_dev(rxCodeBlock.astype(np.float64))
         outCols = k if onlyInfoBits else n
         tdt = _TORCH_F[self.precision]
-        managed = _dev.managed_ok()
+        managed = _dev.managed_ok(c * outCols * z * (8 if outputBelief else 1))
         bits = beliefs = None
         if outputBelief:
             beliefs = (_dev.managed_out((c, outCols * z), np.float64) if managed and self.precision == 'fp64'
@@ -413,12 +415,14 @@ class LdpcDecoder(LdpcBase):
         return _dev.to_host(res).astype(np.float64) if outputBelief else _dev.to_host(res)
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decode2(self, rxCodeBlock, maxIter=6, onlyInfoBits=True, outputBelief=False, alpha=0.75, stopOnGoodParity=True):
+    def decode2(self, rxCodeBlock, maxIter=6, onlyInfoBits=True, outputBelief=False, alpha=0.75, stopOnGoodParity=True,
+                firstRowOnly=False):
         """The reference's undocumented verification decoder (ldpc.py:1421-1492): the same layered schedule walked one
         lifted row at a time, with the true second minimum (no "+100000" term) and a caller-chosen ``alpha``.
         ``stopOnGoodParity`` stops a block after the first iteration whose hard decisions satisfy EVERY parity check; the
         reference's own test looks at the first base-graph row only (``isValidCodedBlock``, ldpc.py:841-843), so with
-        ``stopOnGoodParity=True`` it may stop earlier than this one.  ``lastIterations`` holds the per-block counts."""
+        ``stopOnGoodParity=True`` it may stop earlier than this one; ``firstRowOnly=True`` (compatibility switch) applies
+        the reference's first-row-only stop test instead.  ``lastIterations`` holds the per-block counts."""
         rxCodeBlock = np.asanyarray(rxCodeBlock)      # (keeps a ManagedArray: its pages are read on the device in place)
         c, nIn = rxCodeBlock.shape
         z = self.liftingSize
@@ -436,7 +440,8 @@ class LdpcDecoder(LdpcBase):
         _native.check(_native.lib().nrldpc_decode2(
             _dev.handle(), self.baseGraphNo, z, _native.F64 if x.dtype == torch.float64 else _native.F32,
             _NATIVE_F[self.precision], _dev.ptr(x), c, nIn, nIn // z, int(maxIter), float(alpha),
-            1 if stopOnGoodParity else 0, outCols, _dev.ptr(bits), _dev.ptr(beliefs), _dev.ptr(iters), _dev.stream_ptr()))
+            (2 if firstRowOnly else 1) if stopOnGoodParity else 0, outCols, _dev.ptr(bits), _dev.ptr(beliefs), _dev.ptr(iters),
+            _dev.stream_ptr()))
         self.lastIterations = _dev.to_host(iters)
         out = _dev.to_host(beliefs if outputBelief else bits)
         if onlyInfoBits:
@@ -502,8 +507,10 @@ class LdpcDecoder(LdpcBase):
             key = (txBlockSize, x.shape[1], precision, self.earlyStop, self.earlyStopFrom)
             codec = getattr(self, '_hostCodec', None)
             if codec is None or self._hostCodecKey != key:
+                # (a private library handle: the pipeline issues work on its own streams, include/nrldpc.h allows one handle
+                # per (device, stream); the shared handle stays with the calls on the current stream)
                 codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, x.shape[1], self.txLayers, self.nRef,
-                                     0, precision, self.earlyStop, earlyStopFrom=self.earlyStopFrom)
+                                     0, precision, self.earlyStop, ownHandle=True, earlyStopFrom=self.earlyStopFrom)
                 self._hostCodec, self._hostCodecKey = codec, key
             def unpack(res):
                 self.lastIterations = res['iters'].numpy().reshape(-1)

@@ -21,16 +21,16 @@ import numpy as np
 import ref_loader
 
 
-def run(LdpcEncoder, HarqEntity, Modem, random, toLinear, n, harqType="IR", ebNoDb=3.0, seed=123):
-    modulation, codeRate = "16QAM", 490 / 1024
-    enc = LdpcEncoder(baseGraphNo=1, modulation=modulation, txLayers=1, targetRate=codeRate)
-    harq = HarqEntity(enc, harqType, 16)
+def run(LdpcEncoder, HarqEntity, Modem, random, toLinear, n, harqType="IR", ebNoDb=3.0, seed=123, modulation="16QAM",
+        codeRate=490 / 1024, txLayers=1, tbSize=10000, numProc=16):
+    enc = LdpcEncoder(baseGraphNo=1, modulation=modulation, txLayers=txLayers, targetRate=codeRate)
+    harq = HarqEntity(enc, harqType, numProc)
     snrDb = ebNoDb + 10 * np.log10(enc.qm * codeRate)
     noiseStd = np.sqrt(1 / toLinear(snrDb))
     rangen = random.getGenerator(seed)
     bitgen = random.getGenerator(seed + 1)
     modem = Modem(modulation)
-    sizes = harq.numCW * [10000]
+    sizes = harq.numCW * [tbSize]
     harq.reset()
     lat = []
     for t in range(n):
@@ -78,6 +78,15 @@ def main():
         res["neoradium_b200"]["wall_s"] = time.perf_counter() - t0
         os.environ["NRLDPC_NO_MANAGED"] = "1"       # the same with explicit H2D / D2H copies of the HARQ buffers (round-1 path)
         res["neoradium_b200_no_managed"] = run(LdpcEncoder, harq.HarqEntity, modulation.Modem, rnd.random, utils.toLinear, min(200, args.transmissions))
+        del os.environ["NRLDPC_NO_MANAGED"]
+        # BASELINE configs[2]'s large codeword (256QAM, 4 layers, R = 0.75, A = 176 208: C = 21, Zc = 384; 4.2 MB float64 soft
+        # buffer per HarqCW) below its waterfall, so that most blocks need retransmissions: per-retransmission latency with the
+        # HARQ buffers resident on the device (ManagedArray) and with explicit H2D / D2H copies (round-1 path)
+        big = dict(modulation="256QAM", codeRate=0.75, txLayers=4, tbSize=176208, numProc=4, ebNoDb=9.5)
+        run(LdpcEncoder, harq.HarqEntity, modulation.Modem, rnd.random, utils.toLinear, 8, **big)
+        res["large_slot_managed"] = run(LdpcEncoder, harq.HarqEntity, modulation.Modem, rnd.random, utils.toLinear, 48, **big)
+        os.environ["NRLDPC_NO_MANAGED"] = "1"
+        res["large_slot_no_managed"] = run(LdpcEncoder, harq.HarqEntity, modulation.Modem, rnd.random, utils.toLinear, 48, **big)
         del os.environ["NRLDPC_NO_MANAGED"]
     if args.ref_transmissions > 0:
         t0 = time.perf_counter()

@@ -587,6 +587,58 @@ def test_mixed_slot_256qam_harq_ir_device_soft_buffers():
         assert tbok.all() and np.array_equal(tb[:, :A], pl), "soft combining of four redundancy versions must decode"
 
 
+def test_config2_full_size_grouped_call():
+    """BASELINE configs[2] at FULL size through ONE library call (nrldpc_decode_tb_groups): the 51-RB 256QAM slot of SURVEY 8,
+    codeword 1 = BG1, 4 layers, R = 0.75, A = 176 208 (C = 21, Zc = 384, G = 235 008), codeword 2 = BG2, 2 layers, R = 0.3,
+    A = 37 896 (C = 10, Zc = 384, G = 127 296), incremental redundancy over rv = [0, 2, 3, 1] with DEVICE-resident soft buffers.
+    Every transmission: merged bits, CRC flags and soft buffers equal the C oracle's on the same LLRs and history (fp32), and
+    the grouped call equals two separate calls."""
+    from neoradium_b200.batch import decode_groups
+    rng = np.random.default_rng(51)
+    cw = [dict(bg=1, A=176208, nl=4, g=235008, snr=17.2), dict(bg=2, A=37896, nl=2, g=127296, snr=7.6)]
+    qm, rvs, n_iter, numTb = 8, [0, 2, 3, 1], 6, 1
+    codecs = [{rv: TbBatchCodec(c["bg"], '256QAM', c["A"], c["g"], txLayers=c["nl"], rv=rv, precision='fp32') for rv in set(rvs)}
+              for c in cw]
+    assert (codecs[0][0].C, codecs[0][0].Zc, codecs[1][0].C, codecs[1][0].Zc) == (21, 384, 10, 384)
+    pl = [rng.integers(0, 2, (numTb, c["A"])).astype(np.int8) for c in cw]
+    soft = [torch.zeros((numTb * k[0].C, k[0].ncb - k[0].F), dtype=torch.float32, device='cuda') for k in codecs]
+    soft2 = [torch.zeros_like(x) for x in soft]
+    obuf = [[None] * numTb for _ in cw]
+    tbok_hist = []
+    for k, rv in enumerate(rvs):
+        llr = []
+        for i, c in enumerate(cw):
+            rm_h = codecs[i][rv].encode(torch.from_numpy(pl[i]).cuda()).cpu().numpy()
+            x = np.empty(rm_h.shape, np.float32)
+            for t in range(numTb):
+                assert np.array_equal(rm_h[t], O.tx_chain(pl[i][t], c["bg"], c["g"], qm, c["nl"], 0, rv)[0])
+                x[t] = nr_link.qam_awgn_llr(rm_h[t], qm, c["snr"], rng)
+            llr.append(x)
+        d_llr = [torch.from_numpy(x).cuda() for x in llr]
+        outs = decode_groups([codecs[0][rv], codecs[1][rv]], d_llr, n_iter, softBuffers=soft)
+        sep = [codecs[i][rv].decode(d_llr[i], n_iter, softBuffer=soft2[i]) for i in range(2)]
+        torch.cuda.synchronize()
+        for i, c in enumerate(cw):
+            for key in ("tb", "cbOk", "tbOk", "iters"):
+                assert torch.equal(outs[i][key], sep[i][key]), (k, i, key)
+            assert torch.equal(soft[i], soft2[i])
+            tb, cbok, tbok = (outs[i][key].cpu().numpy() for key in ("tb", "cbOk", "tbOk"))
+            C = codecs[i][0].C
+            soft_h = soft[i].cpu().numpy().reshape(numTb, C, -1)
+            for t in range(numTb):
+                rr, obuf[i][t], p = O.rate_recover(llr[i][t], c["A"], c["bg"], qm, c["nl"], 0, rv, soft_buffer=obuf[i][t], dtype=np.float32)
+                assert np.array_equal(soft_h[t], obuf[i][t]), "soft buffer differs after transmission %d" % k
+                hard = (OC.decode_beliefs(rr, c["bg"], p["Zc"], p["iLS"], n_iter, np.float32)[:, :p["K"]] < 0).astype(np.int8)
+                otb, ocb = O.check_crc_and_merge(hard, p["K"], p["F"], p["C"])
+                assert np.array_equal(tb[t], otb) and list(cbok[t].astype(bool)) == list(ocb)
+                assert bool(tbok[t]) == bool(O.crc_check(otb, '24A'))
+        tbok_hist.append([bool(o["tbOk"].all().item()) for o in outs])
+    assert tbok_hist[0] != [True, True], "the first transmission was meant to fail for at least one codeword"
+    assert tbok_hist[-1] == [True, True], "soft combining of four redundancy versions must decode both codewords"
+    for i in range(2):
+        assert np.array_equal(outs[i]["tb"].cpu().numpy()[:, :cw[i]["A"]], pl[i])
+
+
 def test_async_host_batches_and_concurrent_codecs():
     """Two host batches in flight (decodeLLRsAsync, alternating slots) and two codecs with private handles on two streams
     give exactly the results of the blocking single-stream calls, which equal the oracle's (low SNR: some blocks fail)."""
@@ -665,6 +717,10 @@ def test_decode2_vs_reference_outputs_and_oracle(name):
     assert np.array_equal(bel_s, O.decode2(rr, bg, zc, ils, n_it, False, True, alpha, False))
     if n_it < nit + 4:
         assert O.parity_ok((bel_s[0] < 0).astype(np.int8), bg, zc, ils)
+    # compatibility switch: the reference's own stop test looks at the first base-graph row only (ldpc.py:841-843)
+    bel_f = dec.decode2(rr, nit + 4, False, True, alpha, True, firstRowOnly=True)
+    assert np.array_equal(bel_f, O.decode2(rr, bg, zc, ils, nit + 4, False, True, alpha, True, "first_row"))
+    assert int(dec.lastIterations[0]) <= n_it
     # fp32 arithmetic: same hard decisions on these well-conditioned inputs
     d32 = LdpcDecoder(bg, 'QPSK', 1, 0, precision='fp32')
     d32.initialize(A + 24)

@@ -60,7 +60,7 @@ def test_unmodified_harq_entity_on_dropin_equals_reference_codec(harqType, ebNoD
     assert ent_gpu.txBlocks[1] > 0, "the point is meant to need retransmissions"
 
 
-def test_harq_notebook_statistic_and_device_resident_buffers():
+def test_harq_notebook_statistic_and_device_resident_buffers(monkeypatch):
     """Harq.ipynb raw line 127: at Eb/N0 = 3 dB every first transmission fails and every second one succeeds
     (txBlocks per try [504 496 0 0], rxBlocks [0 496 0 0] for 1000 transmissions; here 96 with 16 processes).  The HARQ
     buffers the unmodified HarqCW holds are ManagedArrays: ndarrays whose pages stay on the device between transmissions."""
@@ -72,6 +72,7 @@ def test_harq_notebook_statistic_and_device_resident_buffers():
     assert res["numTimeouts"] == 0 and abs(res["bler_pct"] - 50.0) < 1e-9
     if not _dev.managed_ok():
         pytest.skip("no concurrent managed access on this device")
+    monkeypatch.setenv("NRLDPC_MANAGED_MIN", "0")     # (the 10 000-bit block of the notebook is below the default size threshold)
     enc = LdpcEncoder(baseGraphNo=1, modulation="16QAM", txLayers=1, targetRate=490 / 1024)
     ent = harq.HarqEntity(enc, "IR", 2)
     rng = np.random.default_rng(0)
