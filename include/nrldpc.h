@@ -235,6 +235,16 @@ int nrldpc_accumulate_counters(nrldpc_handle* h, int64_t num_tb, int C, const ui
                                const uint8_t* tb_crc_ok, const int32_t* iters, const int8_t* tb_bits,
                                const int8_t* ref_bits, int64_t bits_per_tb, int64_t bits_stride, int64_t* counters,
                                nrldpc_stream stream);
+/* the same with separate row pitches for the decoded blocks and the reference payload (no padded copy of the payload) */
+int nrldpc_accumulate_counters_ref(nrldpc_handle* h, int64_t num_tb, int C, const uint8_t* cb_crc_ok,
+                                   const uint8_t* tb_crc_ok, const int32_t* iters, const int8_t* tb_bits, int64_t tb_stride,
+                                   const int8_t* ref_bits, int64_t ref_stride, int64_t bits_per_tb, int64_t* counters,
+                                   nrldpc_stream stream);
+
+/* Payload generator of the on-device link simulator (random.bits, random.py:194, on the device): bit j of the call is bit
+ * (offset + j) of the Philox4x32-10 stream under `seed` (128 bits per counter value), so a sweep draws the same payloads
+ * whatever the batch size or the number of GPUs.  out [n] int8 (0/1). */
+int nrldpc_random_bits(nrldpc_handle* h, uint64_t seed, uint64_t offset, int8_t* out, int64_t n, nrldpc_stream stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Link around the codec, on the device: the producers of the decoder's input in every NeoRadium

@@ -142,6 +142,8 @@ SIGNATURES = {
     "nrldpc_decode_tb_groups": (_i32, [_vp, ctypes.POINTER(TbGroup), _i32, _i32, _i32, _i32, _vp]),
     "nrldpc_check_crc_and_merge": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nrldpc_accumulate_counters": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "nrldpc_accumulate_counters_ref": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _vp]),
+    "nrldpc_random_bits": (_i32, [_vp, ctypes.c_uint64, ctypes.c_uint64, _vp, _i64, _vp]),
     "nrldpc_modulate": (_i32, [_vp, _i32, _vp, _i64, _i32, _vp, _vp]),
     "nrldpc_demap_maxlog": (_i32, [_vp, _i32, _i32, _vp, _i64, ctypes.c_double, _i32, _vp, _vp]),
     "nrldpc_awgn_llr": (_i32, [_vp, _i32, _vp, _i64, ctypes.c_double, ctypes.c_uint64, ctypes.c_uint64, _vp, _vp]),

@@ -94,6 +94,17 @@ class TbBatchCodec:
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
+    def random_payload(self, numTb, seed, firstTb=0, out=None):
+        """int8 [numTb, A] payload bits generated on the device (Philox4x32-10): transport block t of the call is global
+        block firstTb + t of the stream under `seed`, independent of batch size and of the number of GPUs."""
+        if out is None:
+            out = torch.empty((numTb, self.A), dtype=torch.int8, device=self.device)
+        assert out.is_contiguous() and out.shape == (numTb, self.A)
+        _native.check(_native.lib().nrldpc_random_bits(self._h, int(seed) & (2 ** 64 - 1), int(firstTb) * self.A, _dev.ptr(out),
+                                                       numTb * self.A, _dev.stream_ptr()))
+        return out
+
+    # ------------------------------------------------------------------------------------------------------------------
     def alloc_outputs(self, numTb):
         dev = self.device
         return dict(tb=torch.empty((numTb, self.C * self.per), dtype=torch.int8, device=dev),
@@ -189,17 +200,13 @@ class TbBatchCodec:
     def accumulate(self, out, counters, refPayload=None):
         """counters int64[8] += {CBs, CB CRC fails, TBs, TB CRC fails, bit errors, sum iterations, 0, 0}."""
         numTb = out['tb'].shape[0]
-        if refPayload is not None:
-            assert refPayload.shape[1] == self.A and refPayload.stride(0) == self.A
-            # compare the first A bits of each merged block; both are addressed with their own pitch via two calls
-            ref = torch.zeros_like(out['tb'])
-            ref[:, :self.A] = refPayload
-        else:
-            ref = None
-        _native.check(_native.lib().nrldpc_accumulate_counters(
+        ref = refPayload
+        if ref is not None:
+            assert ref.shape[1] == self.A and ref.stride(1) == 1 and ref.dtype == torch.int8
+        _native.check(_native.lib().nrldpc_accumulate_counters_ref(
             self._h, numTb, self.C, _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']), _dev.ptr(out['iters']),
-            _dev.ptr(out['tb']) if ref is not None else None, _dev.ptr(ref), self.A, self.C * self.per,
-            _dev.ptr(counters), _dev.stream_ptr()))
+            _dev.ptr(out['tb']) if ref is not None else None, self.C * self.per, _dev.ptr(ref),
+            ref.stride(0) if ref is not None else 0, self.A, _dev.ptr(counters), _dev.stream_ptr()))
         return counters
 
 

@@ -298,7 +298,8 @@ int launch_bitstream(nrldpc_handle* h, BsArgs& a, cudaStream_t st)
 
 __global__ void nr_counters_kernel(long long numTb, int C, const unsigned char* cbOk, const unsigned char* tbOk,
                                    const int* iters, const signed char* tbBits, const signed char* refBits,
-                                   long long bitsPerTb, long long bitsStride, unsigned long long* counters)
+                                   long long bitsPerTb, long long bitsStride, long long refStride,
+                                   unsigned long long* counters)
 {
     unsigned long long cbFail = 0, tbFail = 0, bitErr = 0, itSum = 0;
     const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,11 +311,17 @@ __global__ void nr_counters_kernel(long long numTb, int C, const unsigned char* 
     }
     if (tbOk)
         for (long long i = gtid; i < numTb; i += gsz) tbFail += tbOk[i] ? 0 : 1;
-    if (tbBits && refBits) {
-        const long long total = numTb * bitsPerTb;
+    if (tbBits && refBits) {   // four bits (bytes) per step where both rows allow an aligned word, single bytes elsewhere
+        const long long W = (bitsPerTb + 3) >> 2, total = numTb * W;
         for (long long i = gtid; i < total; i += gsz) {
-            const long long t = i / bitsPerTb, j = i - t * bitsPerTb;
-            bitErr += ((tbBits[t * bitsStride + j] ^ refBits[t * bitsStride + j]) & 1) ? 1 : 0;
+            const long long t = i / W, j = (i - t * W) << 2;
+            const signed char* pa = tbBits + t * bitsStride + j;
+            const signed char* pb = refBits + t * refStride + j;
+            if (j + 4 <= bitsPerTb && ((reinterpret_cast<uintptr_t>(pa) | reinterpret_cast<uintptr_t>(pb)) & 3) == 0) {
+                bitErr += __popc((*reinterpret_cast<const unsigned int*>(pa) ^ *reinterpret_cast<const unsigned int*>(pb)) & 0x01010101u);
+            } else {
+                for (long long k = j; k < bitsPerTb && k < j + 4; k++) bitErr += ((pa[k - j] ^ pb[k - j]) & 1) ? 1 : 0;
+            }
         }
     }
     // warp reduce then one atomic per warp
@@ -442,13 +449,22 @@ extern "C" int nrldpc_accumulate_counters(nrldpc_handle* h, int64_t num_tb, int 
                                           const int8_t* ref_bits, int64_t bits_per_tb, int64_t bits_stride,
                                           int64_t* counters, nrldpc_stream stream)
 {
+    return nrldpc_accumulate_counters_ref(h, num_tb, C, cb_crc_ok, tb_crc_ok, iters, tb_bits, bits_stride, ref_bits, bits_stride,
+                                          bits_per_tb, counters, stream);
+}
+
+extern "C" int nrldpc_accumulate_counters_ref(nrldpc_handle* h, int64_t num_tb, int C, const uint8_t* cb_crc_ok,
+                                              const uint8_t* tb_crc_ok, const int32_t* iters, const int8_t* tb_bits,
+                                              int64_t tb_stride, const int8_t* ref_bits, int64_t ref_stride,
+                                              int64_t bits_per_tb, int64_t* counters, nrldpc_stream stream)
+{
     if (!h || !counters || num_tb <= 0 || C < 1) { nr_set_error("counters: bad argument"); return NRLDPC_ERR_ARG; }
     NR_CUDA_CHECK(cudaSetDevice(h->device));
-    const long long work = max((long long)num_tb * C, (tb_bits && ref_bits) ? num_tb * bits_per_tb : 0LL);
+    const long long work = max((long long)num_tb * C, (tb_bits && ref_bits) ? num_tb * ((bits_per_tb + 3) / 4) : 0LL);
     const int grid = (int)max(1LL, min((work + 255) / 256, (long long)h->numSMs * 8));
     nr_counters_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(num_tb, C, cb_crc_ok, tb_crc_ok, iters,
                                                                (const signed char*)tb_bits, (const signed char*)ref_bits,
-                                                               bits_per_tb, bits_stride, (unsigned long long*)counters);
+                                                               bits_per_tb, tb_stride, ref_stride, (unsigned long long*)counters);
     NR_CUDA_CHECK(cudaGetLastError());
     return NRLDPC_OK;
 }

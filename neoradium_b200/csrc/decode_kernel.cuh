@@ -509,20 +509,24 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                         }
                     }
                     __syncthreads();
+                    // one base-graph row per warp (lane w < W = the 32 checks 32 w .. 32 w + 31 of that row): the edge-table
+                    // reads are then warp-uniform constant loads.  (One task per THREAD made the lanes of a warp walk three
+                    // different rows -- divergent constant-bank reads, serialised -- and cost a quarter of an iteration.)
                     uint32_t bad = 0;
-                    for (int task = tid; task < a.numRows * W; task += nT) {
-                        const int row = task / W, w = task - row * W;
+                    for (int row = warp; row < a.numRows; row += W) {
                         const int e0 = g.rowEdge0[row];
                         const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
-                        uint32_t acc = (row >= 4) ? pe[(row - 4) * W + w] : 0u;
+                        if (lane < W) {
+                            uint32_t acc = (row >= 4) ? pe[(row - 4) * W + lane] : 0u;
 #pragma unroll 4
-                        for (int e = e0; e < e1; e++) {
-                            const uint32_t raw = g.raw[e];
-                            const uint32_t b = 32u * (uint32_t)w + (raw & 511u);   // first position read by these 32 checks
-                            const uint32_t* pc = pk + (raw >> 9) * 2 * W + (b >> 5);
-                            acc ^= __funnelshift_r(pc[0], pc[1], b & 31u);
+                            for (int e = e0; e < e1; e++) {
+                                const uint32_t raw = g.raw[e];
+                                const uint32_t b = 32u * (uint32_t)lane + (raw & 511u);   // first position read by these 32 checks
+                                const uint32_t* pc = pk + (raw >> 9) * 2 * W + (b >> 5);
+                                acc ^= __funnelshift_r(pc[0], pc[1], b & 31u);
+                            }
+                            bad |= acc;
                         }
-                        bad |= acc;
                     }
                     const int anyBad = __syncthreads_or(bad != 0);
                     if (!anyBad) break;

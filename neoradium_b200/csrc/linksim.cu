@@ -513,3 +513,47 @@ extern "C" int nrldpc_scramble_llrs(nrldpc_handle* h, uint32_t c_init, int dtype
     if (dtype != NRLDPC_F32 && dtype != NRLDPC_F64) { nr_set_error("scramble_llrs: bad dtype"); return NRLDPC_ERR_ARG; }
     return gold_launch(h, dtype == NRLDPC_F32 ? 2 : 3, c_init, num, llrs, out, stream);
 }
+
+// ---- payload bits (include/nrldpc.h, nrldpc_random_bits) ----------------------------------------------------------------
+// one thread = one Philox call = 128 consecutive bits of the global stream, written as int8 0/1
+__global__ void __launch_bounds__(256) nr_random_bits_kernel(unsigned long long seed, unsigned long long offset, signed char* out, long long n)
+{
+    const unsigned long long blk0 = offset >> 7;
+    const long long numBlk = (long long)(((offset + (unsigned long long)n + 127ull) >> 7) - blk0);
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < numBlk; k += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long c = blk0 + (unsigned long long)k;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x62697473u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        const long long j0 = (long long)(c << 7) - (long long)offset;   // index in `out` of the block's first bit
+        if (j0 >= 0 && j0 + 128 <= n && ((reinterpret_cast<uintptr_t>(out + j0) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {   // 16 bits -> 16 bytes
+                const uint32_t h16 = (w[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                uint4 v;
+                v.x = ((h16 >> 0) & 1u) | (((h16 >> 1) & 1u) << 8) | (((h16 >> 2) & 1u) << 16) | (((h16 >> 3) & 1u) << 24);
+                v.y = ((h16 >> 4) & 1u) | (((h16 >> 5) & 1u) << 8) | (((h16 >> 6) & 1u) << 16) | (((h16 >> 7) & 1u) << 24);
+                v.z = ((h16 >> 8) & 1u) | (((h16 >> 9) & 1u) << 8) | (((h16 >> 10) & 1u) << 16) | (((h16 >> 11) & 1u) << 24);
+                v.w = ((h16 >> 12) & 1u) | (((h16 >> 13) & 1u) << 8) | (((h16 >> 14) & 1u) << 16) | (((h16 >> 15) & 1u) << 24);
+                *reinterpret_cast<uint4*>(out + j0 + q * 16) = v;
+            }
+        } else {
+            for (int b = 0; b < 128; b++) {
+                const long long j = j0 + b;
+                if (j >= 0 && j < n) out[j] = (signed char)((w[b >> 5] >> (b & 31)) & 1u);
+            }
+        }
+    }
+}
+
+extern "C" int nrldpc_random_bits(nrldpc_handle* h, uint64_t seed, uint64_t offset, int8_t* out, int64_t n, nrldpc_stream stream)
+{
+    if (!h || !out || n < 0) { nr_set_error("random_bits: bad argument"); return NRLDPC_ERR_ARG; }
+    if (n == 0) return NRLDPC_OK;
+    NR_CUDA_CHECK(cudaSetDevice(h->device));
+    const long long numBlk = (long long)(((offset + (uint64_t)n + 127ull) >> 7) - (offset >> 7));
+    const int grid = (int)max(1LL, min((numBlk + 255) / 256, (long long)h->numSMs * 16));
+    nr_random_bits_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, offset, (signed char*)out, n);
+    NR_CUDA_CHECK(cudaGetLastError());
+    return NRLDPC_OK;
+}

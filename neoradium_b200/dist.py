@@ -42,21 +42,19 @@ def counters_dict(counters):
 def bler_point(codec, num_tb_total, snr_db, num_iter, seed, batch_tbs=64, group=None):
     """One SNR point of a BLER sweep, sharded over the ranks of `group`: payload -> TX chain -> fused QAM + AWGN + max-log
     LLR kernel (`nrldpc_awgn_llr`) -> fused RX chain -> counters, all on the device; returns the globally reduced
-    counters as a dict (same on every rank).  The noise of a symbol depends on (seed, global transport-block index,
-    position) only, so the channel realisation does not change with the number of GPUs or the batch size."""
+    counters as a dict (same on every rank).  Payload bits and the noise of a symbol depend on (seed, global
+    transport-block index, position) only, so the counters do not change with the number of GPUs or the batch size."""
     from .modulation import awgn_llr
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_range(num_tb_total, rank, world)
     dev = codec.device
-    gen = torch.Generator(device=dev)
     counters = torch.zeros(len(COUNTER_NAMES), dtype=torch.int64, device=dev)
     sym_per_tb = codec.sumE // codec.qm
     done = lo
     while done < hi:
         n = min(batch_tbs, hi - done)
-        gen.manual_seed((int(seed) * 1000003 + done) & (2 ** 63 - 1))
-        payload = torch.randint(0, 2, (n, codec.A), dtype=torch.int8, device=dev, generator=gen)
+        payload = codec.random_payload(n, seed=int(seed) ^ 0x5bd1e995, firstTb=done)   # function of the global block index only
         llr = awgn_llr(codec.encode(payload), codec.qm, snr_db=snr_db, seed=seed, offset=done * sym_per_tb)
         out = codec.decode(llr, num_iter)
         codec.accumulate(out, counters, refPayload=payload)

@@ -23,14 +23,12 @@ def test_bler_point_counters_equal_oracle(bg, mod, qm, A, rate, snr, tbs, batch,
     seed = 4242
     d = nd.bler_point(codec, tbs, snr, nit, seed=seed, batch_tbs=batch)
     # the same payloads and noise, regenerated batch by batch exactly as bler_point does, through the oracle
-    gen = torch.Generator(device='cuda')
     sym = codec.sumE // qm
     tb_fail = cb_fail = bit_err = 0
     done = 0
     while done < tbs:
         n = min(batch, tbs - done)
-        gen.manual_seed((seed * 1000003 + done) & (2 ** 63 - 1))
-        pl = torch.randint(0, 2, (n, A), dtype=torch.int8, device='cuda', generator=gen)
+        pl = codec.random_payload(n, seed=seed ^ 0x5bd1e995, firstTb=done)
         llr = awgn_llr(codec.encode(pl), qm, snr_db=snr, seed=seed, offset=done * sym).cpu().numpy()
         plh = pl.cpu().numpy()
         for t in range(n):
@@ -75,3 +73,20 @@ def test_sweep_runner_drives_an_adaptive_scheduler():
     again = BlerSweep(codec, numIter=6, tbsPerPoint=64, batchTbs=32, seed=3).point(pts[-1]["snr_db"])
     for k in ("tbCrcFail", "cbCrcFail", "bitErrors"):            # a point is a pure function of (seed, SNR, sizes)
         assert again[k] == pts[-1][k]
+
+
+def test_payload_generator_and_batch_independence():
+    """nrldpc_random_bits: the payload of a transport block is a function of (seed, global block index) only -- any split of
+    a range into calls gives the same bits (unaligned heads / tails included), bits are balanced, seeds differ; and a BLER
+    point counts the same whatever the batch size (what makes N-GPU counters equal 1-GPU counters)."""
+    codec = TbBatchCodec(2, 'QPSK', 501, 1670, precision='fp32')      # odd A: calls start at unaligned stream offsets
+    whole = codec.random_payload(37, seed=11)
+    parts = torch.cat([codec.random_payload(5, 11, 0), codec.random_payload(1, 11, 5), codec.random_payload(31, 11, 6)])
+    assert torch.equal(whole, parts)
+    assert set(whole.unique().tolist()) == {0, 1} and abs(whole.float().mean().item() - 0.5) < 0.02
+    assert not torch.equal(whole, codec.random_payload(37, seed=12))
+    a = nd.bler_point(codec, 96, -0.8, 6, seed=9, batch_tbs=96)
+    b = nd.bler_point(codec, 96, -0.8, 6, seed=9, batch_tbs=17)
+    for k in ("tbCrcFail", "cbCrcFail", "bitErrors", "sumIterations"):
+        assert a[k] == b[k], k
+    assert 0 < a["tbCrcFail"] < 96
