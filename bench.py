@@ -12,8 +12,9 @@ CRC24B per block -> merge -> CRC24A per transport block) over one such batch: ON
 
   value   whole-job decoded information Gbit/s with the LLRs already resident in HBM (A bits per transport block), two
           batches in flight on two streams; `single_stream` = the same steps back to back on one stream
-  e2e     the same through the host-buffer API (LdpcDecoder.decodeLLRsAsync on pinned host LLRs, two calls in flight,
-          every step's inputs copied H2D and results read back D2H inside the timed region)
+  e2e     the same through the host-buffer API: LdpcDecoder.decodeSymbolsAsync on pinned host complex64 equalised symbols
+          (demapper + fused chain on the device), two calls in flight, every step's inputs copied H2D and results read
+          back D2H inside the timed region; e2e.llr_input = the same with fp32 LLRs of those symbols as the host input
   roofline / cpu_baseline  see DESIGN.md "Measurement"
 The reference arm (--impl reference) times the CPU restatement of the reference's NumPy algorithm (oracle/, pinned
 bit-exact against the unmodified reference) on all host cores; the reference itself is pure Python under
@@ -236,7 +237,7 @@ def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from neoradium_b200 import LdpcDecoder
+    from neoradium_b200 import LdpcDecoder, _dev, _native
     from neoradium_b200.batch import TbBatchCodec
     from neoradium_b200.modulation import awgn_llr
 
@@ -259,13 +260,20 @@ def run_ours(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(SEED + rank)
     NB = 4
-    payloads, llrs = [], []
+    payloads, llrs, syms = [], [], []
+    N0 = 10.0 ** (-SNR_DB / 10.0)
     for b in range(NB):
         pl = torch.randint(0, 2, (tbs, A), dtype=torch.int8, device=dev, generator=gen)
         rm = codec.encode(pl)
         # fused Gray-QAM + AWGN + max-log LLR kernel (nrldpc_awgn_llr), one noise stream per (rank, batch)
         llrs.append(awgn_llr(rm, QM, snr_db=SNR_DB, seed=SEED + 1000 * rank + b, offset=0))
         payloads.append(pl)
+        if b < 2:   # the host-buffer legs start one step further upstream: the equalised symbols of the same code words
+            sym = torch.empty((tbs, G // QM, 2), dtype=torch.float32, device=dev)
+            _native.check(_native.lib().nrldpc_modulate(codec._h, QM, _dev.ptr(rm), tbs * (G // QM), _native.F32, _dev.ptr(sym),
+                                                        _dev.stream_ptr()))
+            sym += torch.randn(sym.shape, dtype=torch.float32, device=dev, generator=gen) * math.sqrt(N0 / 2.0)
+            syms.append(sym)
     out = codec.alloc_outputs(tbs)
     torch.cuda.synchronize()
 
@@ -361,10 +369,18 @@ def run_ours(args):
     #      (a) blocking calls (decodeLLRs returns with the results on the host); (b) the same work with two calls in
     #      flight (decodeLLRsAsync): the H2D copy of step i+1 overlaps the decode and D2H of step i.  Every step copies
     #      its own inputs host->device and its results device->host inside the timed region.
+    #      The LLR legs and the symbol leg carry the SAME channel output: host_sym = complex64 equalised symbols, host_llr =
+    #      their max-log LLRs (nrldpc_demap_maxlog, fp32) -- what Modem.getLLRsFromSymbols hands to the decoder in the reference.
     dec = LdpcDecoder(BG, MOD, 1, 0, precision="fp32")
     host_llr = [torch.empty((tbs, G), dtype=torch.float32).pin_memory() for _ in range(2)]
+    host_sym = [torch.empty((tbs, G // QM), dtype=torch.complex64).pin_memory() for _ in range(2)]
     for j in range(2):
-        host_llr[j].copy_(llrs[j])
+        dl = torch.empty((tbs, G), dtype=torch.float32, device=dev)
+        _native.check(_native.lib().nrldpc_demap_maxlog(codec._h, QM, _native.F32, _dev.ptr(syms[j]), tbs * (G // QM), N0,
+                                                        _native.F32, _dev.ptr(dl), _dev.stream_ptr()))
+        host_llr[j].copy_(dl)
+        host_sym[j].copy_(torch.view_as_complex(syms[j]))
+    del syms
     host_np = [h.numpy() for h in host_llr]
     host_out = [dict(tb=torch.empty((tbs, codec.C * codec.per), dtype=torch.int8).pin_memory(),
                      cbOk=torch.empty((tbs, codec.C), dtype=torch.uint8).pin_memory(),
@@ -397,6 +413,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_ok = e2e_ok and bool(np.array_equal(res[0], payloads[(args.steps - 1) % 2].cpu().numpy())) and bool(res[2].all())
+    ref_bits = [h["tb"].clone() for h in host_out]          # results of the LLR legs for batches 0 / 1 (ordered by slot)
+
+    # ---- the headline end-to-end leg: complex64 equalised symbols in (2 bytes per coded bit at 16QAM instead of 4 for fp32
+    #      LLRs), max-log demapping + fused decode on the device, decoded bits + CRC flags back on the host
+    def run_async_sym(n):
+        pend, last = [], None
+        for i in range(n):
+            pend.append(dec.decodeSymbolsAsync(host_sym[i % 2], N0, A, NUM_ITER, out=host_out[i % 2], slot=i % 2))
+            if len(pend) == 2:
+                last = pend.pop(0).result()
+        while pend:
+            last = pend.pop(0).result()
+        return last
+
+    run_async_sym(4)
+    barrier()
+    t0 = time.perf_counter()
+    res_s = run_async_sym(args.steps)
+    torch.cuda.synchronize()
+    e2es_s = time.perf_counter() - t0
+    jl = (args.steps - 1) % 2
+    e2es_ok = bool(np.array_equal(res_s[0], payloads[jl].cpu().numpy())) and bool(res_s[2].all())
+    sym_equals_llr = bool(torch.equal(host_out[jl]["tb"], ref_bits[jl]))
     # secondary figure: the same host-buffer pipeline fed with the LLRs rounded to IEEE half (NRLDPC_F16 input, widened
     # exactly to fp32 on the device): half the PCIe bytes.  Not the headline -- the workload's LLRs are fp32.
     host16 = [torch.empty((tbs, G), dtype=torch.float16).pin_memory() for _ in range(2)]
@@ -432,13 +471,15 @@ def run_ours(args):
     torch.cuda.synchronize()
     h2d_ms = c0.elapsed_time(c1) / 5
     if world > 1:
-        t = torch.tensor([e2e_s, e2e_sync_s, e2e16_s], dtype=torch.float64, device=dev)
+        t = torch.tensor([e2e_s, e2e_sync_s, e2e16_s, e2es_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s, e2e_sync_s, e2e16_s = float(t[0].item()), float(t[1].item()), float(t[2].item())
+        e2e_s, e2e_sync_s, e2e16_s, e2es_s = float(t[0].item()), float(t[1].item()), float(t[2].item()), float(t[3].item())
     e2e_val = world * tbs * A * args.steps / e2e_s / 1e9
     e2e_sync_val = world * tbs * A * args.steps / e2e_sync_s / 1e9
+    e2es_val = world * tbs * A * args.steps / e2es_s / 1e9
     h2d = tbs * G * 4
-    d2h = tbs * A + tbs * C_PER_TB + tbs + tbs * C_PER_TB * 4
+    h2d_sym = tbs * (G // QM) * 8
+    d2h = tbs * codec.C * codec.per + tbs * C_PER_TB + tbs + tbs * C_PER_TB * 4
 
     if rank != 0:
         if world > 1:
@@ -505,20 +546,28 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world, tbs),
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "LdpcDecoder.decodeLLRsAsync(pinned host fp32 LLRs, out=pinned host buffers), two calls in flight: "
-                           "4-chunk H2D/decode/D2H pipeline per call, every result read back on the host inside the timed region",
-                    "blocking_value": e2e_sync_val,
-                    "blocking_api": "LdpcDecoder.decodeLLRs(...): same pipeline, one call at a time, returns with the results on the host",
-                    "h2d_only_ms_per_step": h2d_ms, "pcie_bound_value": tbs * A / (h2d_ms * 1e-3) / 1e9 * world,
-                    "bits_ok": e2e_ok,
+            "e2e": {"value": e2es_val, "unit": UNIT, "h2d_bytes_per_step": h2d_sym, "d2h_bytes_per_step": d2h,
+                    "api": "LdpcDecoder.decodeSymbolsAsync(pinned host complex64 equalised symbols, noiseVar, out=pinned host buffers), "
+                           "two calls in flight: per call a 4-chunk pipeline H2D -> max-log demapper (nrldpc_demap_maxlog, fp32 LLRs) -> "
+                           "fused rate-recovery/decode/CRC -> D2H; every result is read back on the host inside the timed region",
+                    "input": "what PDSCH.getLLRsFromGrid hands to Modem.getLLRsFromSymbols (pdsch.py:935-1000): 8 bytes per symbol = "
+                             "2 bytes per coded bit at 16QAM instead of 4 for fp32 LLRs",
+                    "bits_ok": e2es_ok, "bits_identical_to_llr_input_leg": sym_equals_llr,
+                    "pcie_bound_value": tbs * A / (h2d_ms * 1e-3 * h2d_sym / h2d) / 1e9 * world,
+                    "llr_input": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  "api": "LdpcDecoder.decodeLLRsAsync(pinned host fp32 LLRs of the same symbols, out=pinned host buffers), "
+                                         "two calls in flight, 4-chunk H2D/decode/D2H pipeline per call (the round-1 headline)",
+                                  "blocking_value": e2e_sync_val,
+                                  "blocking_api": "LdpcDecoder.decodeLLRs(...): same pipeline, one call at a time",
+                                  "h2d_only_ms_per_step": h2d_ms, "pcie_bound_value": tbs * A / (h2d_ms * 1e-3) / 1e9 * world,
+                                  "bits_ok": e2e_ok},
                     "f16_llr_transport": {"value": world * tbs * A * args.steps / e2e16_s / 1e9, "h2d_bytes_per_step": tbs * G * 2,
                                           "bits_ok": e2e16_ok,
-                                          "note": "secondary: same pipeline, host LLRs rounded to IEEE half (NRLDPC_F16 input, "
+                                          "note": "secondary: LLR pipeline, host LLRs rounded to IEEE half (NRLDPC_F16 input, "
                                                   "widened exactly to fp32 on the device)"}},
             "single_stream": {"value": value_serial, "ms_per_step": ms_serial / args.steps,
                               "note": "same K steps launched back to back on ONE stream (no overlap between launches)"},
-            "gpu_launches": args.steps, "gpu_launches_all_timed_regions": args.steps * 2 + n64 + 4 * args.steps * 3,
+            "gpu_launches": args.steps, "gpu_launches_all_timed_regions": args.steps * 2 + n64 + 4 * args.steps * 3 + 8 * args.steps,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "check": {"tb_crc_ok": tb_ok, "tbs": tbs, "payload_bit_errors": bit_err, "two_stream_tb_crc_ok": pipe_ok}}
     emit(line)

@@ -128,7 +128,7 @@ class TbBatchCodec:
         return out
 
     # ------------------------------------------------------------------------------------------------------------------
-    def decode_host(self, llr_host, numIter, out=None, chunks=None, wait=True, slot=0):
+    def decode_host(self, llr_host, numIter, out=None, chunks=None, wait=True, slot=0, noiseVar=None):
         """Host-buffer entry point: llr_host is a float32|float64|float16 [numTb, G'] HOST array (NumPy array or CPU torch
         tensor; pinned memory gives full PCIe speed).  The batch is cut into `chunks` groups of transport blocks and
         pipelined over three CUDA streams -- H2D copy of chunk i+1, fused decode of chunk i and D2H copy of the results of
@@ -140,15 +140,24 @@ class TbBatchCodec:
         ``wait=False`` returns a ``PendingDecode`` right after the work is queued; its ``result()`` blocks until the
         outputs are on the host.  Calls queue behind each other on the same three streams, so with two calls in flight
         (``slot`` 0 / 1 select independent device staging buffers; the caller alternates its host buffers likewise) the
-        H2D copy of the next batch overlaps the decode and D2H of the current one and PCIe never idles."""
+        H2D copy of the next batch overlaps the decode and D2H of the current one and PCIe never idles.
+
+        ``noiseVar`` (with a complex64 [numTb, G'/qm] host array): the input is the EQUALISED SYMBOLS of the codewords, not
+        their LLRs.  The symbols cross PCIe (8 bytes per symbol = 2 bytes per coded bit at 16QAM, 1 at 256QAM, instead of 4
+        for fp32 LLRs) and the max-log demapper (Modem.getLLRsFromSymbols, modulation.py:159-204 -> nrldpc_demap_maxlog,
+        fp32 LLRs) runs on the device in front of the fused decode, chunk by chunk in the same pipeline."""
         x = llr_host if isinstance(llr_host, torch.Tensor) else torch.from_numpy(llr_host)
-        assert x.device.type == 'cpu' and x.dim() == 2 and x.dtype in _IN_DTYPE
+        symbols = x.dtype == torch.complex64
+        assert x.device.type == 'cpu' and x.dim() == 2 and (x.dtype in _IN_DTYPE or symbols)
+        if symbols:
+            assert noiseVar is not None and noiseVar > 0, "symbol input needs the noise variance of the demapper"
+            x = torch.view_as_real(x).reshape(x.shape[0], -1)             # [numTb, 2 * symbols] float32, no copy
         numTb, Gp = x.shape
         if chunks is None:
             chunks = int(os.environ.get("NRLDPC_HOST_CHUNKS", "4"))
         chunks = max(1, min(int(chunks), numTb))
         bounds = [(numTb * i) // chunks for i in range(chunks + 1)]
-        key = (numTb, Gp, x.dtype, chunks)
+        key = (numTb, Gp, x.dtype, chunks, symbols)
         if not hasattr(self, '_streams'):
             self._streams = tuple(torch.cuda.Stream(self.device) for _ in range(3))
             self._pipe = {}
@@ -159,6 +168,8 @@ class TbBatchCodec:
             st = dict(key=key, done=None, h2d=self._streams[0], comp=self._streams[1], d2h=self._streams[2],
                       din=[torch.empty((bounds[i + 1] - bounds[i], Gp), dtype=x.dtype, device=self.device)
                            for i in range(chunks)],
+                      dllr=[torch.empty((bounds[i + 1] - bounds[i], (Gp // 2) * self.qm), dtype=torch.float32, device=self.device)
+                            for i in range(chunks)] if symbols else None,
                       dout=[self.alloc_outputs(bounds[i + 1] - bounds[i]) for i in range(chunks)])
             self._pipe[slot] = st
         if out is None:
@@ -180,7 +191,13 @@ class TbBatchCodec:
                 ev_in.record()
             with torch.cuda.stream(st['comp']):
                 st['comp'].wait_event(ev_in)
-                self.decode(st['din'][i], numIter, out=st['dout'][i])
+                if symbols:
+                    _native.check(_native.lib().nrldpc_demap_maxlog(
+                        self._h, self.qm, _native.F32, _dev.ptr(st['din'][i]), (hi - lo) * (Gp // 2), float(noiseVar),
+                        _native.F32, _dev.ptr(st['dllr'][i]), _dev.stream_ptr()))
+                    self.decode(st['dllr'][i], numIter, out=st['dout'][i])
+                else:
+                    self.decode(st['din'][i], numIter, out=st['dout'][i])
                 ev_done = torch.cuda.Event()
                 ev_done.record()
             with torch.cuda.stream(st['d2h']):

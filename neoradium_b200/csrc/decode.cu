@@ -44,7 +44,7 @@ __global__ void nr_last_nonzero_kernel(const TIn* llr, long long numCb, long lon
 }
 
 template <typename T>
-int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s)
+int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s, bool allowMulti = true)
 {
     const int Z = g.Z;
     a.cbPerCta = max(1, 384 / Z);
@@ -59,17 +59,23 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     size_t miscBytes = ((size_t)((a.cbPerCta + 31) & ~31) + 32 + (size_t)a.cbPerCta * P2) * sizeof(uint32_t) + 16 +
                        (size_t)nT * (sizeof(MinSlot<T>) + sizeof(T));
     // static kernels: mbarriers, CRC factor table, XOR exchange (see the kernel's `extra` region)
-    const bool staticRows = oneCb && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2;
-    if (staticRows) rBytes += (size_t)a.cbPerCta * Z * sizeof(T);   // the dummy row (decode_static.cuh)
+    // statically scheduled kernels: one block per CTA (Zc a multiple of 32, >= 224) or, without early termination, several
+    // blocks per CTA (every other lifting size; decode_kernel.cuh "MB")
+    const bool multiStatic = !oneCb && allowMulti && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2 &&
+                             !(a.flags & NRLDPC_DEC_EARLY_STOP) && Z >= 2 && !getenv("NRLDPC_NO_STATIC_MB");
+    const bool staticRows = (oneCb && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2) || multiStatic;
+    a.nAreas = a.cbPerCta + ((multiStatic && nT > a.cbPerCta * Z) ? 1 : 0);
+    if (staticRows) rBytes = (size_t)a.nAreas * (g.ncore + 1) * Z * sizeof(T);   // + the dummy row (decode_static.cuh)
     a.packWords = 0;
     if (staticRows && (a.flags & NRLDPC_DEC_EARLY_STOP))
-        a.packWords = ((g.ncore * 2 + (a.numRows - 4) + 1) * (nT >> 5) + 3) & ~3;   // +1 row: the funnel shift reads one word past the end
+        a.packWords = (((g.ncore * 2 + (a.numRows - 4) + 1) * (nT >> 5) + 3) & ~3)   // packed bits; +1 row: the funnel shift reads one word past the end
+                      + ((a.numRows * (nT >> 5) + 3) & ~3) + 160 + 160;                 // syndrome words, task list, edge table (decode_kernel.cuh)
     if (staticRows) miscBytes += 16 + 16 + 64 * sizeof(uint32_t) + (size_t)a.packWords * sizeof(uint32_t);
     // target resident CTAs per SM (env NRLDPC_DEC_OCC overrides): two for the fp32 one-block-per-CTA kernel, whose
     // registers are capped at 80 and whose row state lives in Tensor Memory; one otherwise
     // (measured at 17 scheduled rows, profiles/r01_decode_per_lifting_size.json: two resident CTAs lift the generic fp32
     // kernels by 11-45 %, a third one helps only the 7-8 warp CTAs of Zc = 208 / 240)
-    int occ = h->decOcc > 0 ? h->decOcc : (sizeof(T) == 4 ? ((!oneCb && a.cbPerCta == 1 && nT <= 256) ? 3 : 2) : 1);
+    int occ = h->decOcc > 0 ? h->decOcc : (sizeof(T) == 4 ? ((!oneCb && !multiStatic && a.cbPerCta == 1 && nT <= 256) ? 3 : 2) : 1);
     occ = max(1, min(occ, 2048 / nT));
     if (sizeof(T) == 8) occ = 1;
     // static fp32 kernels: when the scheduled rows fit Tensor Memory only with ONE resident CTA (22-42 rows: low code rates,
@@ -87,7 +93,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     a.tmemRows = 0;
     a.tmemCols = 0;
     bool allT = false;
-    if (oneCb && !h->noTmem) {
+    if ((oneCb || multiStatic) && !h->noTmem) {
         int cols = 32;
         while (cols * 2 <= 512 / occ) cols *= 2;
         const int RW = sizeof(T) == 4 ? 4 : 8;
@@ -107,6 +113,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
             a.tmemCols = need;
         }
     }
+    if (multiStatic && !allT && !split) return launch_decode<T>(h, g, a, s, false);   // no such instantiation: generic kernel
     const int restRows = a.numRows - a.tmemRows;
     size_t budget = (size_t)h->smemPerSM / occ - 1024;
     budget = min(budget, (size_t)h->maxSmemOptin);
@@ -124,7 +131,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // TMA staging of the rate-matched stream (fused mode, fp32 stream, no HARQ history): one code block's E LLRs
     a.stageFloats = 0;
     a.crcFacDev = nullptr;
-    if (staticRows && a.rm && (a.tbBits || a.cbCrcOk || a.tbOk)) {
+    if (staticRows && oneCb && a.rm && (a.tbBits || a.cbCrcOk || a.tbOk)) {
         // per-bit CRC constants x^(len-1-i) mod g, i = col*Z + m, laid out [which][col][Z]; which = 0: the code-block CRC over
         // the K-F bits, 1: the CRC24A partial over the payload part (C > 1).  0 beyond the message.
         const int Lk = a.K - a.F, per = (a.C > 1) ? Lk - 24 : Lk;
@@ -152,7 +159,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         }
         a.crcFacDev = (const unsigned int*)h->crcFacDev;
     }
-    if (staticRows && a.rm && !a.softBuf && !a.inF64 && !h->noStage && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) {
+    if (staticRows && oneCb && a.rm && !a.softBuf && !a.inF64 && !h->noStage && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) {
         const int Emax = a.E0 + ((a.nShort < a.C) ? a.fStep : 0);
         const int es = a.inF16 ? 2 : 4, epv = 16 / es;
         const size_t need = ((size_t)((Emax + 2 * (epv - 1)) & ~(epv - 1)) * es + 15) & ~(size_t)15;
@@ -195,6 +202,8 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         const bool bg1 = g.P == NR_BG1_ROWS;
         // preference order: no early-termination code + compile-time table, no early-termination code, everything
         auto try_launch = [&](int esm, int zs) -> cudaError_t {
+            if (multiStatic) return bg1 ? nr_launch_static_bg1_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s)
+                                        : nr_launch_static_bg2_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s);
             if (esm) return bg1 ? nr_launch_static_bg1_es(allt, 1, zs, &dg, &a, (unsigned)grid, nT, smem, s)
                                 : nr_launch_static_bg2_es(allt, 1, zs, &dg, &a, (unsigned)grid, nT, smem, s);
             return bg1 ? nr_launch_static_bg1(allt, 0, zs, &dg, &a, (unsigned)grid, nT, smem, s)

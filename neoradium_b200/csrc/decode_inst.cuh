@@ -1,5 +1,5 @@
 // One group of statically scheduled decoder kernels (see decode_launch.cuh).  The including .cu defines
-//   NR_INST_NAME  launcher name      NR_INST_BG  1 | 2      NR_INST_ES  0 | 1
+//   NR_INST_NAME  launcher name      NR_INST_BG  1 | 2      NR_INST_ES  0 | 1      NR_INST_MB  (defined: several blocks per CTA)
 #include "decode_kernel.cuh"
 #include "decode_launch.cuh"
 
@@ -18,7 +18,11 @@ cudaError_t NR_INST_NAME(int allt, int esm, int zs, const void* dg, const void* 
                          cudaStream_t s)
 {
     constexpr int BG = NR_INST_BG;
-#if NR_INST_ES
+#if defined(NR_INST_MB)
+    if (esm != 0 || zs != 0) return cudaErrorNotSupported;
+    if (allt == 1) return launch_one(nr_decode_kernel<float, false, BG, 1, 0, 0>, dg, da, grid, nT, smem, s);
+    if (allt == 2) return launch_one(nr_decode_kernel<float, false, BG, 2, 0, 0>, dg, da, grid, nT, smem, s);
+#elif NR_INST_ES
     if (esm != 1) return cudaErrorNotSupported;
     if (allt == 1 && zs == 384) return launch_one(nr_decode_kernel<float, true, BG, 1, 1, 384>, dg, da, grid, nT, smem, s);
     if (zs != 0) return cudaErrorNotSupported;

@@ -110,15 +110,21 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
 
     // static kernels: one extra row per block, the per-thread dummy words of the private extension edge (decode_static.cuh)
     constexpr int XROW = (SBG != 0) ? 1 : 0;
-    T* rs = reinterpret_cast<T*>(smemRaw);                                   // [cbPerCta][ncore + XROW][Z]
-    T* stateS = rs + (size_t)cbPerCta * (ncore + XROW) * Z;                  // [smemRows][NPLANES][nT]
+    // MB: statically scheduled kernel with SEVERAL code blocks per CTA (Zc <= 192, and the lifting sizes that are no multiple
+    // of 32).  The row code holds warp-collective instructions (Tensor-Memory loads / stores), so EVERY thread runs it: the
+    // threads that pad the CTA to whole warps, and the blocks of a partly filled last group, work on real shared memory (the
+    // padding threads on a phantom block area of their own) and simply never load or store anything global.
+    constexpr bool MB = (SBG != 0) && !ONE_CB;
+    const int nArea = MB ? a.nAreas : cbPerCta;
+    T* rs = reinterpret_cast<T*>(smemRaw);                                   // [nArea][ncore + XROW][Z]
+    T* stateS = rs + (size_t)nArea * (ncore + XROW) * Z;                     // [smemRows][NPLANES][nT]
     uint32_t* misc = reinterpret_cast<uint32_t*>(stateS + (size_t)a.smemRows * NPLANES * nT);
     // misc: [0, flagsLen) per-block flags | 32 words CRC factors (2 x 16) | per-block CRC trees
     const int flagsLen = (cbPerCta + 31) & ~31;
     uint32_t* fac = misc + flagsLen;
     int P2 = 1;
     while (P2 < Z) P2 <<= 1;
-    uint32_t* tree = misc + flagsLen + 32 + (size_t)cbl * P2;
+    uint32_t* tree = misc + flagsLen + 32 + (size_t)(cbl < cbPerCta ? cbl : cbPerCta - 1) * P2;   // (padding threads never write it)
     // per-thread argmin record + dummy word (16-byte aligned region after the CRC trees)
     const size_t slotOfs = ((size_t)(reinterpret_cast<unsigned char*>(misc + flagsLen + 32 + (size_t)cbPerCta * P2) - smemRaw) + 15) & ~(size_t)15;
     MinSlot<T>* slotP = reinterpret_cast<MinSlot<T>*>(smemRaw + slotOfs) + tid;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     T* rcb = rs + (size_t)cbl * (ncore + XROW) * Z;
     // Tensor Memory for the thread-private row state (see tmem_ld above)
     __shared__ uint32_t tmemBaseSh;
-    const bool useTmem = ONE_CB && a.tmemCols > 0;
+    const bool useTmem = (ONE_CB || MB) && a.tmemCols > 0;
     if (useTmem) {
         if (tid < 32) {
             const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmemBaseSh);
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    StateStore<T, ONE_CB, ALLT> store;
+    StateStore<T, (ONE_CB || MB), ALLT> store;
     {
         const int warp = tid >> 5;
         const uint32_t RW = sizeof(T) == 4 ? 4u : 8u;
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         store.tbase = useTmem ? (tmemBaseSh + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * RW) : 0u;   // lane (warp%4)*32 in bits 31..16
         store.sS = stateS + tid;
         store.sG = stateG + tid;
-        store.tmemRows = ONE_CB ? a.tmemRows : 0;
+        store.tmemRows = (ONE_CB || MB) ? a.tmemRows : 0;
         store.smemRows = a.smemRows;
         store.nT = nT;
     }
@@ -167,7 +173,15 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const uint32_t barLayer = (uint32_t)__cvta_generic_to_shared(extra);
     const uint32_t barStage = barLayer + 8;
     uint32_t* crcRed = reinterpret_cast<uint32_t*>(extra + 16);
-    uint32_t* pk = crcRed + 64;   // bit-packed hard decisions of the early-termination test (a.packWords words)
+    // early-termination test of the static kernels (a.packWords words in all, 0 when the test is off):
+    //   pk [ (2 ncore + numRows - 4 + 1) W ] packed hard decisions | esSyn [numRows W] syndrome words | esTask [160] | esRaw [320 x u16]
+    uint32_t* pk = crcRed + 64;
+    const int esPkWords = (((2 * ncore + (a.numRows - 4) + 1) * (nT >> 5)) + 3) & ~3;
+    const int esSynWords = ((a.numRows * (nT >> 5)) + 3) & ~3;
+    uint32_t* esSyn = pk + esPkWords;
+    uint32_t* esTask = esSyn + esSynWords;
+    uint16_t* esRaw = reinterpret_cast<uint16_t*>(esTask + 160);
+    int esNumTasks = 0;
     float* stage = reinterpret_cast<float*>(pk + ((SBG != 0) ? a.packWords : 0));
     const bool useStage = (SBG != 0) && a.stageFloats > 0;
     LayerBarT<(ALLT == 1 ? NR_DEC_BAR_MODE : (ALLT == 2 ? NR_DEC_BAR_MODE_SPLIT : 0))> lb;
@@ -182,6 +196,17 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const uint32_t mB = (uint32_t)m * 4u;                            // tagged offsets (decode_static.cuh)
     const uint32_t dummyOff2 = mB | ((uint32_t)ncore << 16);         // the thread's word of the dummy row
     const uint32_t rbS = (uint32_t)__cvta_generic_to_shared(rb);
+    if (SBG != 0 && ESM != 0 && a.packWords > 0) {   // task list of the early-termination test: <= 8 core edges of one row each
+        for (int row = 0; row < a.numRows; row++) {
+            const int e0 = g.rowEdge0[row], e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
+            for (int e = e0; e < e1; e += 8) {
+                if (tid == 0) esTask[esNumTasks] = (uint32_t)row | ((uint32_t)e << 8) | ((uint32_t)min(8, e1 - e) << 20) | ((row >= 4 && e == e0) ? (1u << 24) : 0u);
+                esNumTasks++;
+            }
+        }
+        for (int e = tid; e < g.rowEdge0[a.numRows]; e += nT) esRaw[e] = g.raw[e];
+        for (int i = tid; i < a.numRows * (nT >> 5); i += nT) esSyn[i] = 0u;
+    }
     if (SBG != 0) {
         if (tid == 0) {
             liftSh[0] = L2.negZB;
@@ -207,7 +232,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
     const NrCrcPoly polyCb = nr_crc_poly(a.C > 1 ? NRLDPC_CRC24B : NRLDPC_CRC24A);
     const NrCrcPoly polyA = nr_crc_poly(NRLDPC_CRC24A);
     if (wantCrc) {
-        if (SBG == 0) {
+        if (SBG == 0 || MB) {
             crc_factors(fac, Lk, Z, P2, polyCb.poly, polyCb.len, tid);
             if (a.C > 1) crc_factors(fac + 16, per, Z, P2, polyA.poly, polyA.len, tid);
         }
@@ -253,7 +278,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         // -------------------------------------------------------------------------------------------------------
         // load phase: column block `col` (un-punctured index), position m.  Punctured columns 0,1 start at 0.
         // -------------------------------------------------------------------------------------------------------
-        if (active) {
+        if (active || MB) {
             rcb[m] = (T)0;
             rcb[Z + m] = (T)0;
             const int lastCol = ksys + a.numRows;   // exclusive; numRows >= 4
@@ -265,13 +290,13 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 L = a.ncb - a.F;
                 sysLen = a.K - a.F - 2 * Z;
                 Eq = E / a.qm;
-                if (a.softBuf) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
+                if (a.softBuf && active) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
             }
             const int colEnd = (a.rm && sb) ? g.ncols : lastCol;   // a soft buffer is combined over its whole length
             // de-interleaver division i / Eq: float reciprocal + one correction step (exact for i < 2^24)
             const bool smallE = E < (1 << 24);
             const float rcpEq = 1.0f / (float)Eq;
-            const int xAvailI = (int)(xAvail < 0 ? 0 : (xAvail > (long long)E ? (long long)E : xAvail));
+            const int xAvailI = !active ? 0 : (int)(xAvail < 0 ? 0 : (xAvail > (long long)E ? (long long)E : xAvail));   // inactive: nothing is read
             auto load_cols = [&](auto tin) {
                 using TIn = decltype(tin);
                 const TIn* __restrict__ x = reinterpret_cast<const TIn*>(a.llr) + (a.rm ? xBase : cb * a.llrStride);
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 for (int col = 2; col < colEnd; col++, n += Z) {
                     T v = (T)0;
                     if (!a.rm) {
-                        if (col - 2 < a.inCols) v = llr_cvt<T, TIn>(x[n]);
+                        if (active && col - 2 < a.inCols) v = llr_cvt<T, TIn>(x[n]);
                     } else if (n < a.ncb) {
                         if (n >= sysLen && n < sysLen + a.F) {
                             v = (T)1e20;   // filler: LARGE_LLR (chancodebase.py:52), clipped below like any input
@@ -462,14 +487,13 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         bool cbDone = false;
         for (int it = 0; it < a.numIter; it++) {
             if constexpr (SBG != 0) {
-                uint32_t* pe = (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP)) ? pk + (size_t)ncore * 2 * (nT >> 5) : nullptr;
                 RowCtx2<SBG, 0> c0;
                 if (NR_DEC_FIRST_SPECIAL && it == 0) {   // all messages are +0: t = r, no state to read (decode_static.cuh)
                     prep_row2<SBG, 0, ZS, true>(g, mB, L2, store, dummyOff2, c0);
-                    run_rows_static2<SBG, 0, (ESM != 0), ZS, true>(g, a.numRows, rbS, mB, L2, store, slot, dummyOff2, lb, c0, pe);
+                    run_rows_static2<SBG, 0, ZS, true>(g, a.numRows, rbS, mB, L2, store, slot, dummyOff2, lb, c0);
                 } else {
                     prep_row2<SBG, 0, ZS, false>(g, mB, L2, store, dummyOff2, c0);
-                    run_rows_static2<SBG, 0, (ESM != 0), ZS, false>(g, a.numRows, rbS, mB, L2, store, slot, dummyOff2, lb, c0, pe);
+                    run_rows_static2<SBG, 0, ZS, false>(g, a.numRows, rbS, mB, L2, store, slot, dummyOff2, lb, c0);
                 }
             } else {
                 for (int row = 0; row < a.numRows; row++) {
@@ -485,10 +509,11 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             if (!cbDone) itersDone = it + 1;
             if constexpr (SBG != 0) {
                 if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= ((a.flags >> 8) & 0xff)) {
-                    // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed: every warp ballots the sign
-                    // of its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
-                    // neighbouring words); the scheduled extension columns were packed by their rows (run_rows_static); then one thread
-                    // per (row, 32 checks) XORs the shifted words of the row's edges.  ~6 % of an iteration.
+                    // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed.  (1) Every warp ballots the sign of
+                    // its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
+                    // neighbouring words) and of each scheduled extension column (read back from the row state: the row loop
+                    // carries no early-termination code at all).  (2) The XOR of a row's shifted words is cut into tasks of at
+                    // most 8 edges x one 32-check word, one task per thread, merged with shared-memory atomics.  (3) All words 0?
                     const int W = nT >> 5, warp = tid >> 5, lane = tid & 31;
                     uint32_t* pe = pk + (size_t)ncore * 2 * W;   // extension columns, not doubled
                     constexpr int NC = (SBG == 1) ? 26 : 14;   // == ncore (k + 4 columns of degree > 1)
@@ -507,26 +532,36 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                             asm volatile("{.reg .pred p; setp.lt.u32 p, %2, 2; @p st.shared.b32 [%0], %1;}" ::"r"(pAddr), "r"(w), "r"((uint32_t)lane) : "memory");
                             pAddr += pStride;
                         }
+                        uint32_t eAddr = (uint32_t)__cvta_generic_to_shared(pe + warp);
+                        for (int row = 4; row < a.numRows; row++) {
+                            RowState<T> st;
+                            store.load(row, st);
+                            const uint32_t w = __ballot_sync(0xffffffffu, FP<T>::sign(st.rext) != 0);
+                            asm volatile("{.reg .pred p; setp.eq.u32 p, %2, 0; @p st.shared.b32 [%0], %1;}" ::"r"(eAddr), "r"(w), "r"((uint32_t)lane) : "memory");
+                            eAddr += (uint32_t)W * 4u;
+                        }
                     }
                     __syncthreads();
-                    // one base-graph row per warp (lane w < W = the 32 checks 32 w .. 32 w + 31 of that row): the edge-table
-                    // reads are then warp-uniform constant loads.  (One task per THREAD made the lanes of a warp walk three
-                    // different rows -- divergent constant-bank reads, serialised -- and cost a quarter of an iteration.)
-                    uint32_t bad = 0;
-                    for (int row = warp; row < a.numRows; row += W) {
-                        const int e0 = g.rowEdge0[row];
-                        const int e1 = g.rowEdge0[row + 1] - (row >= 4 ? 1 : 0);
-                        if (lane < W) {
-                            uint32_t acc = (row >= 4) ? pe[(row - 4) * W + lane] : 0u;
-#pragma unroll 4
-                            for (int e = e0; e < e1; e++) {
-                                const uint32_t raw = g.raw[e];
-                                const uint32_t b = 32u * (uint32_t)lane + (raw & 511u);   // first position read by these 32 checks
-                                const uint32_t* pc = pk + (raw >> 9) * 2 * W + (b >> 5);
-                                acc ^= __funnelshift_r(pc[0], pc[1], b & 31u);
+                    {
+                        const int w = tid % W, k0 = tid / W, kStep = nT / W;
+                        for (int k = k0; k < esNumTasks; k += kStep) {
+                            const uint32_t tk = esTask[k];            // row | first edge << 8 | edges << 20 | first chunk << 24
+                            const int row = tk & 0xff, e0 = (tk >> 8) & 0xfff, cnt = (tk >> 20) & 0xf;
+                            uint32_t acc = ((tk >> 24) & 1u) ? pe[(row - 4) * W + w] : 0u;
+                            for (int e = e0; e < e0 + cnt; e++) {
+                                const uint32_t raw = esRaw[e];
+                                const uint32_t bpos = 32u * (uint32_t)w + (raw & 511u);   // first position read by these 32 checks
+                                const uint32_t* pc = pk + (raw >> 9) * 2 * W + (bpos >> 5);
+                                acc ^= __funnelshift_r(pc[0], pc[1], bpos & 31u);
                             }
-                            bad |= acc;
+                            if (acc) atomicXor(&esSyn[row * W + w], acc);
                         }
+                    }
+                    __syncthreads();
+                    uint32_t bad = 0;
+                    for (int i = tid; i < a.numRows * W; i += nT) {
+                        bad |= esSyn[i];
+                        esSyn[i] = 0u;   // ready for the next test (ordered by the barriers around the accumulation)
                     }
                     const int anyBad = __syncthreads_or(bad != 0);
                     if (!anyBad) break;
@@ -575,30 +610,33 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 T* o = reinterpret_cast<T*>(a.beliefs) + cb * (long long)a.outCols * Z;
                 for (int col = 0; col < outCore; col++) o[col * Z + m] = rcb[col * Z + m];
             }
-            for (int col = ncore; col < a.outCols; col++) {
-                const int row = col - ksys;
-                T v;
-                if (row < a.numRows) {
-                    RowState<T> st;
-                    store.load(row, st);
-                    v = st.rext;
-                } else {
-                    // skipped row: t_ext == 0 in every iteration, so its belief after the last iteration is
-                    // 0.75 * parity * min(min_j |r_j|, 1e5) over the row's core edges evaluated on the final posteriors
-                    const int e0 = g.rowEdge0[row];
-                    const int e1 = g.rowEdge0[row + 1] - 1;
-                    T mn = (T)100000;
-                    uint32_t par = 0;
-                    for (int e = e0; e < e1; e++) {
-                        T rv;
-                        if constexpr (SBG != 0) rv = (T)edge_posterior2(g, e, rbS, mB, L2);
-                        else rv = edge_posterior<T>(g, e, rb, mU, ZB);
-                        mn = FP<T>::mn(mn, FP<T>::abs(rv));
-                        par ^= FP<T>::sign(rv);
-                    }
-                    v = (a.numIter > 0) ? FP<T>::flip(FP<T>::mul(mn, (T)0.75), par) : (T)0;
-                    v = FP<T>::add(v, (T)0);
+        }
+        // extension columns: the state reads are warp-collective in the Tensor-Memory kernels, so every thread takes them
+        for (int col = ncore; col < a.outCols; col++) {
+            const int row = col - ksys;
+            T v = (T)0;
+            if (row < a.numRows) {
+                RowState<T> st;
+                store.load(row, st);
+                v = st.rext;
+            } else if (active) {
+                // skipped row: t_ext == 0 in every iteration, so its belief after the last iteration is
+                // 0.75 * parity * min(min_j |r_j|, 1e5) over the row's core edges evaluated on the final posteriors
+                const int e0 = g.rowEdge0[row];
+                const int e1 = g.rowEdge0[row + 1] - 1;
+                T mn = (T)100000;
+                uint32_t par = 0;
+                for (int e = e0; e < e1; e++) {
+                    T rv;
+                    if constexpr (SBG != 0) rv = (T)edge_posterior2(g, e, rbS, mB, L2);
+                    else rv = edge_posterior<T>(g, e, rb, mU, ZB);
+                    mn = FP<T>::mn(mn, FP<T>::abs(rv));
+                    par ^= FP<T>::sign(rv);
                 }
+                v = (a.numIter > 0) ? FP<T>::flip(FP<T>::mul(mn, (T)0.75), par) : (T)0;
+                v = FP<T>::add(v, (T)0);
+            }
+            if (active) {
                 if (a.bits) a.bits[cb * a.bitsStride + col * Z + m] = (signed char)(v < (T)0);
                 if (a.beliefs) reinterpret_cast<T*>(a.beliefs)[cb * (long long)a.outCols * Z + col * Z + m] = v;
             }
@@ -606,7 +644,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         if (wantCrc) {
             // checkCrcAndMerge (ldpc.py:1610-1619) on the hard decisions still in shared memory
             uint32_t remCb, remA;
-            if constexpr (SBG != 0) {
+            if constexpr (SBG != 0 && ONE_CB) {
                 // CRC by linearity: remainder = XOR over the set bits i of x^(len-1-i) mod g.  Thread m owns bit col*Z + m of
                 // every systematic column; the per-bit constants come from a per-configuration table in global memory
                 // ([2][ksys][Z] words, L2-resident, coalesced; 0 beyond the message, so fillers and the CRC24A/B length

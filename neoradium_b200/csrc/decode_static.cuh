@@ -233,18 +233,12 @@ __device__ __forceinline__ void process_row2(const NrDecGraph& g, RowCtx2<BG, RO
     }
 }
 
-template <int BG, int ROW, bool ES, int ZS, bool FIRST, typename Store, typename LayerBar>
+template <int BG, int ROW, int ZS, bool FIRST, typename Store, typename LayerBar>
 __device__ __forceinline__ void run_rows_static2(const NrDecGraph& g, int numRows, uint32_t rbS, uint32_t mB, const Lift2& L,
                                                  const Store& store, uint32_t slot, uint32_t dummyOff, LayerBar& lb,
-                                                 RowCtx2<BG, ROW>& cur, uint32_t* pe)
+                                                 RowCtx2<BG, ROW>& cur)
 {
     process_row2<BG, ROW, ZS, FIRST>(g, cur, rbS, slot, dummyOff, L);
-    if constexpr (ES && ROW >= 4) {
-        if (pe) {   // early termination: packed hard decisions of this row's private extension column (see the kernel)
-            const uint32_t w = __ballot_sync(0xffffffffu, FP<float>::sign(cur.st.rext) != 0);
-            if ((threadIdx.x & 31) == 0) pe[(ROW - 4) * (blockDim.x >> 5) + (threadIdx.x >> 5)] = w;
-        }
-    }
     lb.arrive();
     store.store(ROW, cur.st);
     if constexpr (ROW + 1 < BgRows<BG>::P) {
@@ -256,7 +250,7 @@ __device__ __forceinline__ void run_rows_static2(const NrDecGraph& g, int numRow
         prep_row2<BG, ROW + 1, ZS, FIRST>(g, mB, L, store, dummyOff, nxt);
         pregather_row2<BG, ROW + 1, ZS>(g, rbS, L, nxt);
         lb.wait();
-        run_rows_static2<BG, ROW + 1, ES, ZS, FIRST>(g, numRows, rbS, mB, L, store, slot, dummyOff, lb, nxt, pe);
+        run_rows_static2<BG, ROW + 1, ZS, FIRST>(g, numRows, rbS, mB, L, store, slot, dummyOff, lb, nxt);
     } else {
         lb.wait();
     }

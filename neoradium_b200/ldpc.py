@@ -478,8 +478,26 @@ class LdpcDecoder(LdpcBase):
             raise ValueError("decodeLLRsAsync takes a [numTb, G] host batch")
         return self.decodeLLRs(llrs, txBlockSize, numIter, out=out, _async=int(slot))
 
+    def decodeSymbolsAsync(self, symbols, noiseVar, txBlockSize, numIter=5, out=None, slot=0):
+        """``decodeLLRsAsync`` one step further upstream (extension): ``symbols`` is a complex64 [numTb, G/qm] HOST batch of
+        equalised symbols (what PDSCH.getLLRsFromGrid hands to Modem.getLLRsFromSymbols, pdsch.py:935-1000), ``noiseVar``
+        the demapper's noise variance.  The symbols cross PCIe (2 bytes per coded bit at 16QAM, 1 at 256QAM, instead of 4
+        for fp32 LLRs); max-log demapping (modulation.py:159-204) and the fused rate-recovery / decode / CRC chain run on
+        the device.  LLRs are computed in float64 from the float32 symbol coordinates and rounded to float32 (a few ulp from
+        the reference's float64 demapper, tests/test_gpu_link.py); decoding is the fp32 chain.  Same result tuple and
+        in-flight rules as ``decodeLLRsAsync``."""
+        isT = isinstance(symbols, torch.Tensor)
+        x = symbols if isT else torch.from_numpy(np.ascontiguousarray(symbols))
+        if x.dim() != 2 or x.device.type != 'cpu' or x.dtype != torch.complex64:
+            raise ValueError("decodeSymbolsAsync takes a complex64 [numTb, G/qm] host batch")
+        return self.decodeLLRs(x, txBlockSize, numIter, out=out, _async=int(slot), _noiseVar=float(noiseVar))
+
+    def decodeSymbols(self, symbols, noiseVar, txBlockSize, numIter=5, out=None):
+        """Blocking form of ``decodeSymbolsAsync``."""
+        return self.decodeSymbolsAsync(symbols, noiseVar, txBlockSize, numIter, out=out).result()
+
     def decodeLLRs(self, llrs, txBlockSize, numIter=5, harq=None, precision=None, returnDevice=False, out=None,
-                   _async=None):
+                   _async=None, _noiseVar=None):
         """Fused RX chain (extension; the operation sequence of HarqCW.decodeLLRs, harq.py:165-173):
         recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A') in one kernel pass.
 
@@ -501,15 +519,16 @@ class LdpcDecoder(LdpcBase):
         onHost = (not isT) or llrs.device.type == 'cpu'
         hdt = llrs.dtype if isT else np.asarray(llrs).dtype
         if (not single) and onHost and harq is None and not returnDevice and \
-                hdt in (torch.float32, torch.float64, torch.float16, np.float32, np.float64, np.float16):
+                hdt in (torch.float32, torch.float64, torch.float16, torch.complex64, np.float32, np.float64, np.float16):
             from .batch import TbBatchCodec
             x = llrs if isT else np.ascontiguousarray(llrs)
-            key = (txBlockSize, x.shape[1], precision, self.earlyStop, self.earlyStopFrom)
+            gBits = x.shape[1] * (self.qm if _noiseVar is not None else 1)
+            key = (txBlockSize, gBits, precision, self.earlyStop, self.earlyStopFrom)
             codec = getattr(self, '_hostCodec', None)
             if codec is None or self._hostCodecKey != key:
                 # (a private library handle: the pipeline issues work on its own streams, include/nrldpc.h allows one handle
                 # per (device, stream); the shared handle stays with the calls on the current stream)
-                codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, x.shape[1], self.txLayers, self.nRef,
+                codec = TbBatchCodec(self.baseGraphNo, self.modulation, txBlockSize, gBits, self.txLayers, self.nRef,
                                      0, precision, self.earlyStop, ownHandle=True, earlyStopFrom=self.earlyStopFrom)
                 self._hostCodec, self._hostCodecKey = codec, key
             def unpack(res):
@@ -517,9 +536,9 @@ class LdpcDecoder(LdpcBase):
                 return (res['tb'].numpy()[:, :txBlockSize], res['cbOk'].numpy().view(np.bool_),
                         res['tbOk'].numpy().view(np.bool_))
             if _async is not None:
-                pend = codec.decode_host(x, numIter, out=out, wait=False, slot=_async)
+                pend = codec.decode_host(x, numIter, out=out, wait=False, slot=_async, noiseVar=_noiseVar)
                 return _PendingLLRs(pend, unpack)
-            return unpack(codec.decode_host(x, numIter, out=out))
+            return unpack(codec.decode_host(x, numIter, out=out, noiseVar=_noiseVar))
         x = _dev.to_dev(llrs)
         if x.dtype not in (torch.float32, torch.float64, torch.float16):
             x = x.to(torch.float64)

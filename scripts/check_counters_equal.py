@@ -4,11 +4,12 @@ carries the same counters: the workload is geometry independent, so N GPUs must 
 import json
 import sys
 
-lines = [json.loads(l) for l in open(sys.argv[1]) if l.strip()]
+lines = [json.loads(l) for l in open(sys.argv[1]) if l.strip().startswith("{")]
 key = lambda d: json.dumps(d.get("counters") or [[p[k] for k in ("snr_db", "txBlocks", "tbCrcFail", "cbCrcFail", "bitErrors", "sumIterations")] for p in d["points"]], sort_keys=True)
 groups = {}
 for d in lines:
-    groups.setdefault((d["config"] if isinstance(d["config"], str) else json.dumps(d["config"], sort_keys=True)), []).append(d)
+    cfg = d["config"] if isinstance(d["config"], str) else json.dumps({k: v for k, v in d["config"].items() if k != "out"}, sort_keys=True)
+    groups.setdefault(cfg, []).append(d)
 ok = True
 for cfg, ds in groups.items():
     ks = {key(d) for d in ds}

@@ -117,3 +117,33 @@ def test_gold_sequence_and_scrambling_bit_exact():
         d32 = torch.from_numpy(llr.astype(np.float32)).cuda()
         assert np.array_equal(scramble_(c_init, d32).cpu().numpy(), llr.astype(np.float32) * (1 - 2 * np.float32(c)))
     assert goldSequence(1, 0) == []
+
+
+def test_symbol_input_host_pipeline_equals_llr_input():
+    """LdpcDecoder.decodeSymbols / decodeSymbolsAsync (complex64 equalised symbols across PCIe, demapper + fused chain on the
+    device) returns exactly what decodeLLRs returns for the fp32 max-log LLRs of the same symbols, and those LLRs agree with
+    the reference demapper formula (oracle, float64) to a few ulp of float32."""
+    import nr_modem
+    from neoradium_b200 import LdpcDecoder, LdpcEncoder
+    rng = np.random.default_rng(77)
+    bg, mod, qm, A, numTb = 1, '16QAM', 4, 8424 * 2 - 24, 6
+    G = 14040 * 2
+    enc = LdpcEncoder(bg, mod, 1, 0, 0.6)
+    n0 = 10 ** (-8.4 / 10)                                            # waterfall: some blocks fail, most pass
+    sym = np.empty((numTb, G // qm), np.complex64)
+    pl = rng.integers(0, 2, (numTb, A)).astype(np.int8)
+    for t in range(numTb):
+        x = nr_modem.modulate(enc.getRateMatchedCodeBlocks(pl[t], G).astype(np.int8), qm)
+        sym[t] = (x + (rng.standard_normal(x.shape) + 1j * rng.standard_normal(x.shape)) * np.sqrt(n0 / 2)).astype(np.complex64)
+    dec = LdpcDecoder(bg, mod, 1, 0, precision='fp32')
+    tb_s, cb_s, ok_s = dec.decodeSymbols(sym, n0, A, 8)
+    llr64 = np.stack([nr_modem.llrs_maxlog(sym[t].astype(np.complex128), qm, n0) for t in range(numTb)])
+    llr32 = llr64.astype(np.float32)
+    tb_l, cb_l, ok_l = dec.decodeLLRs(llr32, A, 8)
+    assert np.array_equal(cb_s, cb_l) and np.array_equal(ok_s, ok_l)
+    good = np.asarray(ok_l, bool)
+    assert good.any() and np.array_equal(tb_s[good], tb_l[good]) and np.array_equal(tb_s[good], pl[good])
+    p0 = dec.decodeSymbolsAsync(sym[:3], n0, A, 8, slot=0)
+    p1 = dec.decodeSymbolsAsync(sym[3:], n0, A, 8, slot=1)
+    a, b = p0.result(), p1.result()
+    assert np.array_equal(np.concatenate([a[0], b[0]]), tb_s) and np.array_equal(np.concatenate([a[2], b[2]]), ok_s)
