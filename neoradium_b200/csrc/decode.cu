@@ -64,7 +64,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     const bool multiStatic = !oneCb && allowMulti && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2 &&
                              !(a.flags & NRLDPC_DEC_EARLY_STOP) && Z >= 2 && !getenv("NRLDPC_NO_STATIC_MB");
     const bool staticRows = (oneCb && sizeof(T) == 4 && !h->noStaticRows && !a.trueMin2) || multiStatic;
-    a.nAreas = a.cbPerCta + ((multiStatic && nT > a.cbPerCta * Z) ? 1 : 0);
+    a.nAreas = multiStatic ? (nT + Z - 1) / Z : a.cbPerCta;   // padding threads: tid / Z can reach past cbPerCta by more than one (Zc < 16)
     if (staticRows) rBytes = (size_t)a.nAreas * (g.ncore + 1) * Z * sizeof(T);   // + the dummy row (decode_static.cuh)
     a.packWords = 0;
     if (staticRows && (a.flags & NRLDPC_DEC_EARLY_STOP))

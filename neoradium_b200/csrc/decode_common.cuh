@@ -30,7 +30,7 @@ struct DecArgs {
     // batch
     long long numCb;
     int cbPerCta;       // code blocks hosted by one CTA
-    int nAreas;         // multi-block static kernels: posterior areas in shared memory (cbPerCta, +1 phantom area for padding threads)
+    int nAreas;         // multi-block static kernels: posterior areas in shared memory = ceil(threads / Zc) (phantom areas for padding threads)
     int numIter;
     int flags;
     int numRows;        // rows scheduled (>= 4); rows >= numRows have all-zero extension LLRs

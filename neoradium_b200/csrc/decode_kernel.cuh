@@ -15,7 +15,12 @@ namespace {
 //   ALLT = 1: every scheduled row in Tensor Memory (no tier branches);  ALLT = 2 ("split"): rows [0, kSplitRows) in Tensor
 //   Memory at the same fixed stride, every further scheduled row in the shared-memory planes -- the tier of a row is then
 //   known at compile time in the static schedule (22-33 scheduled rows with two resident CTAs, i.e. code rates ~0.4-0.54)
-template <typename T, bool ONE_CB, int ALLT>
+//   WSYNC (multi-block static kernels): a __syncwarp() in front of every Tensor-Memory access.  tcgen05.ld / st are
+//   warp-collective (.sync.aligned) but reach the compiler as opaque inline asm: around thread-varying conditions (the padding
+//   threads of a multi-block CTA differ from their warp mates in `active` and in the soft-buffer pointer) it is free to unswitch
+//   or duplicate the code that holds them, which leaves part of a warp at one copy and the rest at another -- a hang.  The
+//   convergent intrinsic pins the code (no unswitching across it) and re-converges the warp at run time.
+template <typename T, bool ONE_CB, int ALLT, bool WSYNC = false>
 struct StateStore {
     uint32_t tbase;     // this thread's TMEM address of row slot 0 (lane quadrant and warp column offset folded in)
     uint32_t tstride;   // TMEM columns per row slot
@@ -28,6 +33,7 @@ struct StateStore {
     static constexpr int kSplitRows = 21;   // 256 TMEM columns / kAllTStride (fp32)
     __device__ __forceinline__ void load(int row, RowState<T>& st) const
     {
+        if constexpr (WSYNC) __syncwarp();
         if constexpr (ALLT == 1) {
             tmem_ld(st, tbase + (uint32_t)row * kAllTStride);
             return;
@@ -46,6 +52,7 @@ struct StateStore {
     }
     __device__ __forceinline__ void store(int row, const RowState<T>& st) const
     {
+        if constexpr (WSYNC) __syncwarp();
         if constexpr (ALLT == 1) {
             tmem_st(st, tbase + (uint32_t)row * kAllTStride);
             return;
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    StateStore<T, (ONE_CB || MB), ALLT> store;
+    StateStore<T, (ONE_CB || MB), ALLT, MB> store;
     {
         const int warp = tid >> 5;
         const uint32_t RW = sizeof(T) == 4 ? 4u : 8u;
@@ -292,7 +299,9 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
                 Eq = E / a.qm;
                 if (a.softBuf && active) sb = reinterpret_cast<T*>(a.softBuf) + cb * (long long)L;
             }
-            const int colEnd = (a.rm && sb) ? g.ncols : lastCol;   // a soft buffer is combined over its whole length
+            // (uniform conditions only: `sb` is null for the padding threads of a multi-block CTA, and the paths below hold
+            // warp-collective Tensor-Memory stores)
+            const int colEnd = (a.rm && a.softBuf) ? g.ncols : lastCol;   // a soft buffer is combined over its whole length
             // de-interleaver division i / Eq: float reciprocal + one correction step (exact for i < 2^24)
             const bool smallE = E < (1 << 24);
             const float rcpEq = 1.0f / (float)Eq;
@@ -390,7 +399,7 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
             };
             if (useStage && E <= L) {
                 if (a.inF16) staged_load(__half()); else staged_load(float());
-            } else if (a.rm && !sb && !a.inF64 && !a.inF16 && smallE) {
+            } else if (a.rm && !a.softBuf && !a.inF64 && !a.inF16 && smallE) {
                 // common case (fp32 stream, no HARQ history): same arithmetic, none of the generic bookkeeping
                 const float* __restrict__ x = reinterpret_cast<const float*>(a.llr) + xBase;
                 const int ncb = a.ncb, F = a.F, k0 = a.k0, qm = a.qm;

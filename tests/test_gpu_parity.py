@@ -639,6 +639,37 @@ def test_config2_full_size_grouped_call():
         assert np.array_equal(outs[i]["tb"].cpu().numpy()[:, :cw[i]["A"]], pl[i])
 
 
+@pytest.mark.timeout(180)
+def test_multi_block_static_kernels_equal_generic_kernels(monkeypatch):
+    """Statically scheduled kernels with SEVERAL code blocks per CTA (every lifting size that is no multiple of 32 or is
+    below 224): padding threads (Zc = 8, 11, 22, 30: up to 21 of 32), a partly filled last group, C > 1 (CRC24B + the in-kernel
+    transport-block CRC), soft buffers (the load path must not depend on the per-thread soft-buffer pointer), LBRM with
+    k0 beyond the buffer, IEEE-half input.  Bit-identical to the generic (run-time row dispatch) kernels, which the rest of
+    the suite pins to the oracle."""
+    from neoradium_b200.modulation import awgn_llr
+    cases = [(2, 500, 'QPSK', 1668, 23, 0, 0), (1, 600, '16QAM', 1200, 7, 0, 1), (2, 24, 'QPSK', 100, 130, 0, 0),
+             (1, 9000, '16QAM', 18000, 5, 0, 0), (2, 100, 'QPSK', 600, 9, 400, 3), (2, 40, 'QPSK', 200, 3, 0, 1),
+             (1, 3000, '64QAM', 6000, 2, 0, 2)]
+    for bg, A, mod, g, numTb, nref, rv in cases:
+        codec = TbBatchCodec(bg, mod, A, g, 1, nref, rv, 'fp32')
+        x = awgn_llr(codec.encode(codec.random_payload(numTb, 3)), codec.qm, snr_db=2.0 * codec.qm, seed=1)
+        out = codec.decode(x, 6)
+        soft = torch.zeros((numTb * codec.C, codec.ncb - codec.F), dtype=torch.float32, device='cuda')
+        out_s = codec.decode(x, 6, softBuffer=soft)
+        out_h = codec.decode(x.half().float(), 6)
+        out_h16 = codec.decode(x.half(), 6)
+        torch.cuda.synchronize()
+        monkeypatch.setenv("NRLDPC_NO_STATIC_MB", "1")
+        ref_codec = TbBatchCodec(bg, mod, A, g, 1, nref, rv, 'fp32', ownHandle=True)
+        soft_r = torch.zeros_like(soft)
+        ref, ref_s = ref_codec.decode(x, 6), ref_codec.decode(x, 6, softBuffer=soft_r)
+        torch.cuda.synchronize()
+        monkeypatch.delenv("NRLDPC_NO_STATIC_MB")
+        for k in ('tb', 'cbOk', 'tbOk', 'iters'):
+            assert torch.equal(out[k], ref[k]) and torch.equal(out_s[k], ref_s[k]) and torch.equal(out_h[k], out_h16[k]), (bg, A, k)
+        assert torch.equal(soft, soft_r)
+
+
 def test_async_host_batches_and_concurrent_codecs():
     """Two host batches in flight (decodeLLRsAsync, alternating slots) and two codecs with private handles on two streams
     give exactly the results of the blocking single-stream calls, which equal the oracle's (low SNR: some blocks fail)."""
