@@ -107,3 +107,38 @@ def test_unmodified_snr_scheduler_drives_the_sweep():
     by_snr = sorted(pts, key=lambda p: p["snr_db"])
     assert by_snr[0]["bler"] == 1.0 and by_snr[-1]["bler"] == 0.0
     assert all(a["bler"] >= b["bler"] - 0.05 for a, b in zip(by_snr, by_snr[1:]))   # monotone up to sampling noise
+
+
+def test_polar_crc_reuse():
+    """The Polar codec inherits the CRC API from ChanCodeBase (polar.py:117, 235, 524, 973-977).  With the three classmethods
+    patched to the CUDA ones the reference's Polar encoder / SCL decoder produce exactly what they
+    produce with their own CRC: segmentation with appendCrc (1-D blocks), list decoding with checkCrc on the 2-D candidate
+    matrix, for the DCI ('24C'), UCI ('11' / '6') configurations."""
+    polar, rnd = ref_loader.load_reference("polar", "random")
+    from neoradium_b200 import ChanCodeBase as GpuCrc
+    rng = np.random.default_rng(5)
+
+    class GpuPolarEncoder(polar.PolarEncoder):
+        appendCrc = GpuCrc.appendCrc
+        checkCrc = GpuCrc.checkCrc
+        getCrc = GpuCrc.getCrc
+
+    class GpuPolarDecoder(polar.PolarDecoder):
+        appendCrc = GpuCrc.appendCrc
+        checkCrc = GpuCrc.checkCrc
+        getCrc = GpuCrc.getCrc
+
+    for dataType, payload, e in (("DCI", 40, 216), ("UCI", 30, 120), ("UCI", 16, 40)):
+        msg = rng.integers(0, 2, payload).astype(np.int8)
+        outs = []
+        for Enc, Dec in ((polar.PolarEncoder, polar.PolarDecoder), (GpuPolarEncoder, GpuPolarDecoder)):
+            enc = Enc(payload, e, dataType)
+            cbs = enc.doSegmentation(msg)
+            rm = enc.rateMatch(enc.encode(cbs))
+            llr = (1.0 - 2.0 * rm) * 4.0 + np.random.default_rng(9).standard_normal(rm.shape) * 1.2     # [C, E]
+            dec = Dec(payload, e, dataType)
+            decoded, crcErrors = dec.decode(dec.recoverRate(llr))
+            outs.append((np.asarray(cbs), np.asarray(rm), np.asarray(decoded), crcErrors))
+        for a, b in zip(outs[0], outs[1]):
+            assert np.array_equal(a, b), dataType
+        assert np.array_equal(outs[1][2], msg) and outs[1][3] == 0
