@@ -509,8 +509,8 @@ def run_ours(args):
                 "sm_mhz": sm_mhz, "edge_updates_per_s": edge_rate,
                 "kernel": "nr_decode_kernel<float, ONE_CB, BG1, all-TMEM, Zc=384>", "kernel_ms": kern_ms,
                 "kernel_ms_source": "CUDA events around each launch of the single-stream pass (one kernel per step, launches do not overlap there)",
-                "traffic": 58.26e6 * ncb / 1024.0,
-                "traffic_source": "ncu --set full: dram read 57.70 MB + write 0.56 MB per 1024-block launch (profiles/)",
+                "traffic": 58.30e6 * ncb / 1024.0,
+                "traffic_source": "ncu --set full (profiles/r02_decode_ncu_metrics.csv, r2b): dram read 57.74 MB + write 0.55 MB per 1024-block launch",
                 "two_stream_frac": (world * tbs * C_PER_TB * args.steps / world) * EDGE_UPDATES_PER_CB * 10 / (ms_total * 1e-3) / lane_rate,
                 "executed": {"edge_updates_per_block": EXECUTED_EDGE_UPDATES_PER_CB, "edge_updates_per_s": exec_rate,
                              "frac": exec_rate * 10 / lane_rate,
@@ -548,7 +548,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world, tbs),
             "e2e": {"value": e2es_val, "unit": UNIT, "h2d_bytes_per_step": h2d_sym, "d2h_bytes_per_step": d2h,
                     "api": "LdpcDecoder.decodeSymbolsAsync(pinned host complex64 equalised symbols, noiseVar, out=pinned host buffers), "
-                           "two calls in flight: per call a 4-chunk pipeline H2D -> max-log demapper (nrldpc_demap_maxlog, fp32 LLRs) -> "
+                           "two calls in flight: per call a 2-chunk pipeline H2D -> max-log demapper (nrldpc_demap_maxlog, fp32 LLRs) -> "
                            "fused rate-recovery/decode/CRC -> D2H; every result is read back on the host inside the timed region",
                     "input": "what PDSCH.getLLRsFromGrid hands to Modem.getLLRsFromSymbols (pdsch.py:935-1000): 8 bytes per symbol = "
                              "2 bytes per coded bit at 16QAM instead of 4 for fp32 LLRs",
@@ -556,7 +556,7 @@ def run_ours(args):
                     "pcie_bound_value": tbs * A / (h2d_ms * 1e-3 * h2d_sym / h2d) / 1e9 * world,
                     "llr_input": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                   "api": "LdpcDecoder.decodeLLRsAsync(pinned host fp32 LLRs of the same symbols, out=pinned host buffers), "
-                                         "two calls in flight, 4-chunk H2D/decode/D2H pipeline per call (the round-1 headline)",
+                                         "two calls in flight, 2-chunk H2D/decode/D2H pipeline per call (the round-1 headline)",
                                   "blocking_value": e2e_sync_val,
                                   "blocking_api": "LdpcDecoder.decodeLLRs(...): same pipeline, one call at a time",
                                   "h2d_only_ms_per_step": h2d_ms, "pcie_bound_value": tbs * A / (h2d_ms * 1e-3) / 1e9 * world,
