@@ -83,17 +83,30 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // (measured: BG2 all rows 635 -> 773, 30 rows BG1 705 -> 775 G edge-updates/s); beyond 42 rows two spilling CTAs win
     // ... unless the rows beyond the 21 that fit 256 TMEM columns fit the shared-memory planes of two resident CTAs: the
     // "split" kernels keep both CTAs and know every row's tier at compile time
-    bool split = false;
-    if (staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
+    // CTAs of at most 8 warps (Zc <= 256; no early termination): THREE per SM, each with 128 Tensor-Memory columns = 16 rows at two
+    // warps per lane quadrant; further rows in shared-memory planes when they fit a third of the SM ("w8" instantiations)
+    bool w8 = false, w8AllT = false;
+    if (staticRows && sizeof(T) == 4 && nT <= 256 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && h->decOcc <= 0 && !h->noTmem &&
+        !getenv("NRLDPC_NO_W8")) {
+        const size_t budget3 = min((size_t)h->smemPerSM / 3 - 1024, (size_t)h->maxSmemOptin);
+        w8AllT = a.numRows <= 16;
+        w8 = rBytes + miscBytes + (size_t)(w8AllT ? 0 : a.numRows - 16) * rowBytes <= budget3;
+        if (w8) occ = 3;
+    }
+    bool split = w8 && !w8AllT;
+    if (!w8 && staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
         const size_t budget2 = min((size_t)h->smemPerSM / 2 - 1024, (size_t)h->maxSmemOptin);
         split = rBytes + miscBytes + (size_t)(a.numRows - 21) * rowBytes <= budget2;
     }
-    if (!split && staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
+    if (!w8 && !split && staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
     // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs
     a.tmemRows = 0;
     a.tmemCols = 0;
-    bool allT = false;
-    if ((oneCb || multiStatic) && !h->noTmem) {
+    bool allT = w8 && w8AllT;
+    if (w8) {
+        a.tmemRows = a.numRows < 16 ? a.numRows : 16;
+        a.tmemCols = 128;
+    } else if ((oneCb || multiStatic) && !h->noTmem) {
         int cols = 32;
         while (cols * 2 <= 512 / occ) cols *= 2;
         const int RW = sizeof(T) == 4 ? 4 : 8;
@@ -196,12 +209,14 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // few %); a compile-time edge table (SpecTab) exists for the largest lifting size (no table operands in front of a row)
     const bool z384 = sizeof(T) == 4 && Z == 384 && !getenv("NRLDPC_NO_SPECZ");
     const bool noEs = sizeof(T) == 4 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && !getenv("NRLDPC_ES_CODE");
-    if (split && (a.tmemRows != 21 || a.smemRows != a.numRows - 21)) { nr_set_error("decode: internal error (split state layout)"); return NRLDPC_ERR_ARG; }
+    if (split && (a.tmemRows != (w8 ? 16 : 21) || a.smemRows != a.numRows - (w8 ? 16 : 21))) { nr_set_error("decode: internal error (split state layout)"); return NRLDPC_ERR_ARG; }
     if (staticRows) {
         const int allt = split ? 2 : (allT ? 1 : 0);
         const bool bg1 = g.P == NR_BG1_ROWS;
         // preference order: no early-termination code + compile-time table, no early-termination code, everything
         auto try_launch = [&](int esm, int zs) -> cudaError_t {
+            if (w8) return bg1 ? nr_launch_static_bg1_w8(allt, oneCb ? 1 : 0, &dg, &a, (unsigned)grid, nT, smem, s)
+                               : nr_launch_static_bg2_w8(allt, oneCb ? 1 : 0, &dg, &a, (unsigned)grid, nT, smem, s);
             if (multiStatic) return bg1 ? nr_launch_static_bg1_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s)
                                         : nr_launch_static_bg2_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s);
             if (esm) return bg1 ? nr_launch_static_bg1_es(allt, 1, zs, &dg, &a, (unsigned)grid, nT, smem, s)

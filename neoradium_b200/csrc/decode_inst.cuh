@@ -14,6 +14,17 @@ cudaError_t launch_one(K kern, const void* dg, const void* da, unsigned grid, in
 }
 }   // namespace
 
+#if defined(NR_INST_W8)
+cudaError_t NR_INST_NAME(int allt, int oneCb, const void* dg, const void* da, unsigned grid, int nT, size_t smem, cudaStream_t s)
+{
+    constexpr int BG = NR_INST_BG;
+    if (oneCb && allt == 1) return launch_one(nr_decode_kernel<float, true, BG, 1, 0, 0, 2>, dg, da, grid, nT, smem, s);
+    if (oneCb && allt == 2) return launch_one(nr_decode_kernel<float, true, BG, 2, 0, 0, 2>, dg, da, grid, nT, smem, s);
+    if (!oneCb && allt == 1) return launch_one(nr_decode_kernel<float, false, BG, 1, 0, 0, 2>, dg, da, grid, nT, smem, s);
+    if (!oneCb && allt == 2) return launch_one(nr_decode_kernel<float, false, BG, 2, 0, 0, 2>, dg, da, grid, nT, smem, s);
+    return cudaErrorNotSupported;
+}
+#else
 cudaError_t NR_INST_NAME(int allt, int esm, int zs, const void* dg, const void* da, unsigned grid, int nT, size_t smem,
                          cudaStream_t s)
 {
@@ -38,3 +49,4 @@ cudaError_t NR_INST_NAME(int allt, int esm, int zs, const void* dg, const void* 
 #endif
     return cudaErrorNotSupported;
 }
+#endif

@@ -20,7 +20,9 @@ namespace {
 //   threads of a multi-block CTA differ from their warp mates in `active` and in the soft-buffer pointer) it is free to unswitch
 //   or duplicate the code that holds them, which leaves part of a warp at one copy and the rest at another -- a hang.  The
 //   convergent intrinsic pins the code (no unswitching across it) and re-converges the warp at run time.
-template <typename T, bool ONE_CB, int ALLT, bool WSYNC = false>
+//   WPQ: warps per Tensor-Memory lane quadrant of the ALLT / split layouts: 3 (CTAs of up to 12 warps, two per SM, 256 columns
+//   each: 21 rows) or 2 (CTAs of up to 8 warps, THREE per SM, 128 columns each: 16 rows)
+template <typename T, bool ONE_CB, int ALLT, bool WSYNC = false, int WPQ = 3>
 struct StateStore {
     uint32_t tbase;     // this thread's TMEM address of row slot 0 (lane quadrant and warp column offset folded in)
     uint32_t tstride;   // TMEM columns per row slot
@@ -29,8 +31,8 @@ struct StateStore {
     int tmemRows, smemRows, nT;
     // ALLT: every scheduled row lives in Tensor Memory at a compile-time stride (3 warps per lane quadrant): no tier
     // branches, and with a static row index the TMEM address is base + immediate
-    static constexpr uint32_t kAllTStride = 3u * (sizeof(T) == 4 ? 4u : 8u);   // referenced by the ALLT instantiations only
-    static constexpr int kSplitRows = 21;   // 256 TMEM columns / kAllTStride (fp32)
+    static constexpr uint32_t kAllTStride = (uint32_t)WPQ * (sizeof(T) == 4 ? 4u : 8u);   // referenced by the ALLT instantiations only
+    static constexpr int kSplitRows = WPQ == 3 ? 21 : 16;   // 256 / 128 TMEM columns / kAllTStride (fp32)
     __device__ __forceinline__ void load(int row, RowState<T>& st) const
     {
         if constexpr (WSYNC) __syncwarp();
@@ -101,8 +103,8 @@ __device__ __forceinline__ T load_llr(const void* p, long long i, int f64)
 // ---------------------------------------------------------------------------------------------------------------
 // ESM (static kernels): 1 = the early-termination code is compiled in (run-time flag), 0 = left out altogether
 //      ZS (static kernels without the early-termination code): lifting size known at compile time (SpecTab), 0 = run time
-template <typename T, bool ONE_CB, int SBG, int ALLT, int ESM = 1, int ZS = 0>
-__global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
+template <typename T, bool ONE_CB, int SBG, int ALLT, int ESM = 1, int ZS = 0, int WPQ = 3>
+__global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ == 2 ? 3 : NR_DEC_MIN_CTAS) : 1))
     nr_decode_kernel(const __grid_constant__ NrDecGraph g, const __grid_constant__ DecArgs a)
 {
     extern __shared__ __align__(16) unsigned char smemRaw[];
@@ -153,11 +155,11 @@ __global__ void __launch_bounds__(384, (sizeof(T) == 4 ? NR_DEC_MIN_CTAS : 1))
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    StateStore<T, (ONE_CB || MB), ALLT, MB> store;
+    StateStore<T, (ONE_CB || MB), ALLT, MB, WPQ> store;
     {
         const int warp = tid >> 5;
         const uint32_t RW = sizeof(T) == 4 ? 4u : 8u;
-        const uint32_t wpq = ALLT != 0 ? 3u : ((uint32_t)((nT >> 5) + 3) >> 2);   // warps per lane quadrant
+        const uint32_t wpq = ALLT != 0 ? (uint32_t)WPQ : ((uint32_t)((nT >> 5) + 3) >> 2);   // warps per lane quadrant
         store.tstride = wpq * RW;
         store.tbase = useTmem ? (tmemBaseSh + ((uint32_t)(warp & 3) << 21) + (uint32_t)(warp >> 2) * RW) : 0u;   // lane (warp%4)*32 in bits 31..16
         store.sS = stateS + tid;

@@ -20,3 +20,9 @@ cudaError_t nr_launch_static_bg1_mb(int allt, int esm, int zs, const void* decGr
                                     size_t smem, cudaStream_t s);
 cudaError_t nr_launch_static_bg2_mb(int allt, int esm, int zs, const void* decGraph, const void* decArgs, unsigned grid, int nT,
                                     size_t smem, cudaStream_t s);
+// CTAs of at most 8 warps (Zc <= 256), three per SM, 128 Tensor-Memory columns each: allt 1 (<= 16 rows) | 2 (16 rows in TMEM, the
+// rest in shared planes); esm 0, zs 0; `oneCb` selects the one-block-per-CTA or the multi-block instantiation
+cudaError_t nr_launch_static_bg1_w8(int allt, int oneCb, const void* decGraph, const void* decArgs, unsigned grid, int nT,
+                                    size_t smem, cudaStream_t s);
+cudaError_t nr_launch_static_bg2_w8(int allt, int oneCb, const void* decGraph, const void* decArgs, unsigned grid, int nT,
+                                    size_t smem, cudaStream_t s);
