@@ -145,6 +145,54 @@ __global__ void __launch_bounds__(CRC_THREADS)
         const bool srcAligned = ((reinterpret_cast<uintptr_t>(src) & 7) == 0);
         const bool dstAligned = dst && ((reinterpret_cast<uintptr_t>(dst) & 7) == 0);
         const bool maskCopy = (a.mode == BS_SEGMENT);   // doSegmentation writes bit values (ldpc.py:1011-1030)
+        // ---- phase 1, 16-byte form (source and destination 16-byte aligned at the segment start: every block-structured
+        //      caller): a lane moves 16 values per step with one 128-bit load / store and packs them into two bytes -- half
+        //      the steps of the 8-byte form below (the kernel is bound by instruction issue, not by HBM) ----
+        const bool wide = ((reinterpret_cast<uintptr_t>(src + o0) & 15) == 0) && (!dst || ((reinterpret_cast<uintptr_t>(dst + o0) & 15) == 0));
+        if (wide) {
+            constexpr int U2 = (U > 1) ? U / 2 : 1;
+            for (int i0 = lane * 16; i0 < nbits; i0 += 512 * U2) {
+                uint4 w[U2];
+#pragma unroll
+                for (int u = 0; u < U2; u++) {
+                    const int i = i0 + u * 512;
+                    const long long o = o0 + i;
+                    w[u] = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < nbits) {
+                        if (o + 16 <= avail) {
+                            w[u] = *reinterpret_cast<const uint4*>(src + o);
+                        } else {
+                            unsigned char* wb = reinterpret_cast<unsigned char*>(&w[u]);
+                            for (int k = 0; k < 16; k++)
+                                if (o + k < avail) wb[k] = (unsigned char)src[o + k];
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U2; u++) {
+                    const int i = i0 + u * 512;
+                    const long long o = o0 + i;
+                    if (i >= nbits) break;
+                    if (dst && o < copyLen) {
+                        uint4 wo = w[u];
+                        if (maskCopy) { wo.x &= 0x01010101u; wo.y &= 0x01010101u; wo.z &= 0x01010101u; wo.w &= 0x01010101u; }
+                        if (o + 16 <= copyLen) {
+                            *reinterpret_cast<uint4*>(dst + o) = wo;
+                        } else {
+                            const unsigned char* wb = reinterpret_cast<const unsigned char*>(&wo);
+                            for (int k = 0; k < 16 && o + k < copyLen; k++) dst[o + k] = (signed char)wb[k];
+                        }
+                    }
+                    if (wantCrc) {
+                        uint32_t pa = pack8(make_uint2(w[u].x, w[u].y)), pb = pack8(make_uint2(w[u].z, w[u].w));
+                        if (i + 8 > nbits) pa &= 0xFF00u >> (nbits - i);           // bits beyond the stream end never enter the CRC
+                        if (i + 8 >= nbits) pb = 0u;
+                        else if (i + 16 > nbits) pb &= 0xFF00u >> (nbits - i - 8);
+                        *reinterpret_cast<unsigned short*>(&pk[warp][i >> 3]) = (unsigned short)((pa & 0xFFu) | ((pb & 0xFFu) << 8));
+                    }
+                }
+            }
+        } else
         // ---- phase 1: load 8 values per lane, copy out, pack; four loads in flight per lane (a warp works through its
         //      segment alone, so the memory-level parallelism has to come from here) ----
         for (int i0 = lane * 8; i0 < nbits; i0 += 256 * U) {
