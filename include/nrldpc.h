@@ -184,6 +184,11 @@ int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dt
 int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr, int64_t num_cb,
                    int64_t llr_stride, int in_cols, int max_iter, double alpha, int stop_on_good_parity, int out_cols,
                    int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
+/* the same with an OFFSET on top of the normalisation (extension; SURVEY 8f row 4 -- the reference has only the normalised
+ * form): |message| = max(alpha * min - beta, 0), beta >= 0; beta = 0 is nrldpc_decode2. */
+int nrldpc_decode2_offset(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr, int64_t num_cb,
+                          int64_t llr_stride, int in_cols, int max_iter, double alpha, double beta, int stop_on_good_parity,
+                          int out_cols, int8_t* bits, void* beliefs, int32_t* iters, nrldpc_stream stream);
 
 /* Fused RX chain: recoverRate -> decode -> checkCrcAndMerge -> checkCrc('24A'), i.e. HarqCW.decodeLLRs
  * (harq.py:165-173) / the documented usage ldpc.py:1234-1251, in ONE kernel per code-block group: rate recovery is

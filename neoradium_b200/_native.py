@@ -137,6 +137,8 @@ SIGNATURES = {
                              _vp]),
     "nrldpc_decode2": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, ctypes.c_double, _i32, _i32, _vp,
                               _vp, _vp, _vp]),
+    "nrldpc_decode2_offset": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _i64, _i64, _i32, _i32, ctypes.c_double, ctypes.c_double, _i32,
+                                     _i32, _vp, _vp, _vp, _vp]),
     "nrldpc_decode_tb": (_i32, [_vp, _cfgp, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp,
                                 _vp, _vp, _vp]),
     "nrldpc_decode_tb_groups": (_i32, [_vp, ctypes.POINTER(TbGroup), _i32, _i32, _i32, _i32, _vp]),

@@ -319,11 +319,20 @@ extern "C" int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, in
                               int stop_on_good_parity, int out_cols, int8_t* bits, void* beliefs, int32_t* iters,
                               nrldpc_stream stream)
 {
+    return nrldpc_decode2_offset(h, bg, zc, in_dtype, compute_dtype, llr, num_cb, llr_stride, in_cols, max_iter, alpha, 0.0,
+                                 stop_on_good_parity, out_cols, bits, beliefs, iters, stream);
+}
+
+extern "C" int nrldpc_decode2_offset(nrldpc_handle* h, int bg, int zc, int in_dtype, int compute_dtype, const void* llr,
+                                     int64_t num_cb, int64_t llr_stride, int in_cols, int max_iter, double alpha, double beta,
+                                     int stop_on_good_parity, int out_cols, int8_t* bits, void* beliefs, int32_t* iters,
+                                     nrldpc_stream stream)
+{
     if (!h) { nr_set_error("decode2: null handle"); return NRLDPC_ERR_ARG; }
     NrGraph g;
     if (nr_build_graph(bg, zc, &g)) return NRLDPC_ERR_ARG;
     if (num_cb <= 0 || in_cols < 0 || in_cols > g.ncols - 2 || out_cols < 1 || out_cols > g.ncols || max_iter < 0 ||
-        llr_stride < (int64_t)in_cols * zc || !(alpha == alpha)) {
+        llr_stride < (int64_t)in_cols * zc || !(alpha == alpha) || !(beta >= 0.0)) {
         nr_set_error("decode2: bad arguments");
         return NRLDPC_ERR_ARG;
     }
@@ -343,6 +352,7 @@ extern "C" int nrldpc_decode2(nrldpc_handle* h, int bg, int zc, int in_dtype, in
     a.numRows = g.P;          // every row: the closed form of skipped rows is specific to the standard rule
     a.trueMin2 = 1;
     a.alpha = alpha;
+    a.beta = beta;
     a.synRows = (stop_on_good_parity == 2) ? 1 : 0;   // 2: the reference's first-row-only stop test (ldpc.py:841-843, 1483-1485)
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, (cudaStream_t)stream);
 }

@@ -74,6 +74,7 @@ struct DecArgs {
     // decode2 (ldpc.py:1421-1492): true second minimum and a caller-chosen alpha; generic kernels only
     int trueMin2;
     double alpha;
+    double beta;        // offset min-sum (extension): |message| = max(alpha * min - beta, 0); 0 = normalised min-sum (the reference)
     int synRows;        // generic kernels: rows of the early-termination syndrome (0 = all scheduled rows; 1 = decode2 compatibility)
     // static kernels with NRLDPC_DEC_EARLY_STOP: words of the bit-packed hard decisions (multiple of 4), see the kernel
     int packWords;
@@ -361,7 +362,7 @@ __device__ __forceinline__ void row_offsets(const NrDecGraph& g, int e0, uint32_
 template <typename T, int D, bool EXT, uint32_t PRE = 0>
 __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* __restrict__ rb, RowState<T>& st,
                                                uint32_t slot, uint32_t dummyOff, float onef, bool stdRule = true,
-                                               T alpha = (T)0.75, const float* pre = nullptr)
+                                               T alpha = (T)0.75, const float* pre = nullptr, T beta = (T)0)
 {
     // PRE (static fp32 schedule): bit j set = the posterior of edge j was gathered ahead of the layer barrier into pre[j]
     // (its column is not touched by the previous row, see run_rows_static)
@@ -481,6 +482,10 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
     const uint32_t msw = par ? (~nsw & ((1u << D) - 1u)) : nsw;   // sign of new message j = sign_j * parity
     m1s = FP<T>::mul(min1, alpha);
     m2s = FP<T>::mul(min2, alpha);
+    if (beta != (T)0) {   // offset min-sum (extension of decode2; the reference has only the normalised form)
+        m1s = FP<T>::mx(FP<T>::sub(m1s, beta), (T)0);
+        m2s = FP<T>::mx(FP<T>::sub(m2s, beta), (T)0);
+    }
     // parity folded into the two candidates by an exact multiplication with +-1 (an XOR here would be re-associated
     // by ptxas into one extra LOP3 per edge)
     const T psign = FP<T>::flip((T)1, par);
@@ -512,35 +517,35 @@ __device__ __forceinline__ void process_row_at(const uint32_t (&off)[D], char* _
 
 template <typename T, int D, bool EXT>
 __device__ __forceinline__ void process_row(const NrDecGraph& g, int e0, char* __restrict__ rb, uint32_t m,
-                                            Lift ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha)
+                                            Lift ZB, RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha, T beta = (T)0)
 {
     uint32_t off[D];
     row_offsets<D, EXT>(g, e0, m, ZB, dummyOff, off);
-    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff, g.onef, stdRule, alpha);
+    process_row_at<T, D, EXT>(off, rb, st, slot, dummyOff, g.onef, stdRule, alpha, nullptr, beta);
 }
 
 template <typename T>
 __device__ __forceinline__ void dispatch_row(const NrDecGraph& g, int row, char* rb, uint32_t m, Lift ZB,
-                                             RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha)
+                                             RowState<T>& st, uint32_t slot, uint32_t dummyOff, bool stdRule, T alpha, T beta = (T)0)
 {
     const int e0 = g.rowEdge0[row];
     const int deg = g.rowEdge0[row + 1] - e0;
     if (row >= 4) {
         switch (deg) {
-            case 3: process_row<T, 3, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 4: process_row<T, 4, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 5: process_row<T, 5, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 6: process_row<T, 6, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 7: process_row<T, 7, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 8: process_row<T, 8, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 9: process_row<T, 9, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            default: process_row<T, 10, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 3: process_row<T, 3, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 4: process_row<T, 4, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 5: process_row<T, 5, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 6: process_row<T, 6, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 7: process_row<T, 7, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 8: process_row<T, 8, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 9: process_row<T, 9, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            default: process_row<T, 10, true>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
         }
     } else {
         switch (deg) {
-            case 8: process_row<T, 8, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            case 10: process_row<T, 10, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
-            default: process_row<T, 19, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha); break;
+            case 8: process_row<T, 8, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            case 10: process_row<T, 10, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
+            default: process_row<T, 19, false>(g, e0, rb, m, ZB, st, slot, dummyOff, stdRule, alpha, beta); break;
         }
     }
 }

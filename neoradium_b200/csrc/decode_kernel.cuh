@@ -511,7 +511,7 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
                     if (ONE_CB || (active && !cbDone)) {
                         RowState<T> st;
                         store.load(row, st);
-                        dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff, !a.trueMin2, a.trueMin2 ? (T)a.alpha : (T)0.75);
+                        dispatch_row<T>(g, row, rb, mU, ZB, st, slot, dummyOff, !a.trueMin2, a.trueMin2 ? (T)a.alpha : (T)0.75, a.trueMin2 ? (T)a.beta : (T)0);
                         store.store(row, st);
                     }
                     __syncthreads();

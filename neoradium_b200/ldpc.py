@@ -416,13 +416,14 @@ class LdpcDecoder(LdpcBase):
 
     # ------------------------------------------------------------------------------------------------------------------
     def decode2(self, rxCodeBlock, maxIter=6, onlyInfoBits=True, outputBelief=False, alpha=0.75, stopOnGoodParity=True,
-                firstRowOnly=False):
+                firstRowOnly=False, beta=0.0):
         """The reference's undocumented verification decoder (ldpc.py:1421-1492): the same layered schedule walked one
         lifted row at a time, with the true second minimum (no "+100000" term) and a caller-chosen ``alpha``.
         ``stopOnGoodParity`` stops a block after the first iteration whose hard decisions satisfy EVERY parity check; the
         reference's own test looks at the first base-graph row only (``isValidCodedBlock``, ldpc.py:841-843), so with
         ``stopOnGoodParity=True`` it may stop earlier than this one; ``firstRowOnly=True`` (compatibility switch) applies
-        the reference's first-row-only stop test instead.  ``lastIterations`` holds the per-block counts."""
+        the reference's first-row-only stop test instead.  ``beta`` > 0 (extension) turns the rule into offset min-sum,
+        |message| = max(alpha * min - beta, 0).  ``lastIterations`` holds the per-block counts."""
         rxCodeBlock = np.asanyarray(rxCodeBlock)      # (keeps a ManagedArray: its pages are read on the device in place)
         c, nIn = rxCodeBlock.shape
         z = self.liftingSize
@@ -437,9 +438,9 @@ class LdpcDecoder(LdpcBase):
         else:
             bits = torch.empty((c, outCols * z), dtype=torch.int8, device=x.device)
         iters = torch.empty((c,), dtype=torch.int32, device=x.device)
-        _native.check(_native.lib().nrldpc_decode2(
+        _native.check(_native.lib().nrldpc_decode2_offset(
             _dev.handle(), self.baseGraphNo, z, _native.F64 if x.dtype == torch.float64 else _native.F32,
-            _NATIVE_F[self.precision], _dev.ptr(x), c, nIn, nIn // z, int(maxIter), float(alpha),
+            _NATIVE_F[self.precision], _dev.ptr(x), c, nIn, nIn // z, int(maxIter), float(alpha), float(beta),
             (2 if firstRowOnly else 1) if stopOnGoodParity else 0, outCols, _dev.ptr(bits), _dev.ptr(beliefs), _dev.ptr(iters),
             _dev.stream_ptr()))
         self.lastIterations = _dev.to_host(iters)

@@ -338,7 +338,7 @@ def decode(rx, bg, zc, ils, num_iter=5, only_info=True, output_belief=False, dty
 # a12  decode2: the row-by-row verification decoder  (ldpc.py:1421-1492)
 # ---------------------------------------------------------------------------------------------------------------------
 def decode2(rx, bg, zc, ils, max_iter=6, only_info=True, output_belief=False, alpha=0.75, stop_on_good_parity=False,
-            stop_rule="all", K=None):
+            stop_rule="all", K=None, beta=0.0):
     """[C, N] LLRs -> bits int8 / float64 beliefs, one lifted parity-check row at a time, exactly as the reference walks
     them (row = i*Z + m, edges in ascending column order, column index col*Z + (m + V) % Z, ldpc.py:1434-1445):
         t = rx[cols] - rr;  a = |t|;  j* = first argmin;  min1 = a[j*];  min2 = min_{j != j*} a_j      (:1462-1470)
@@ -346,6 +346,7 @@ def decode2(rx, bg, zc, ils, max_iter=6, only_info=True, output_belief=False, al
         min1 == 0 < min2 : rr_j* = prod(1 - 2 (t < 0)) * min2 * alpha, other rr_j = 0                  (:1478-1481)
         both zero : rr = 0                                                                           (:1482-1483)
         rx[cols] = t + rr                                                                            (:1485)
+    `beta` (extension, the reference has none): offset min-sum, |message| = max(alpha * min - beta, 0).
     `stop_rule`: "all" = stop after an iteration whose hard decisions satisfy every check (what the CUDA path does);
     "first_row" = what the reference actually tests (isValidCodedBlock returns after the first base-graph row,
     ldpc.py:841-843).  float64 like the reference."""
@@ -377,10 +378,14 @@ def decode2(rx, bg, zc, ils, max_iter=6, only_info=True, output_belief=False, al
                     new = s1 * min1
                     new[js] = s1[js] * min2
                     new = new * alpha
+                    if beta:    # offset min-sum (extension, not in the reference): |message| = max(alpha * min - beta, 0)
+                        new = np.sign(new) * np.maximum(np.abs(new) - beta, 0.0)
                 elif min2 > 0:
                     new = np.zeros_like(t)
                     new[js] = np.prod(1 - 2 * (t < 0)) * min2
                     new = new * alpha
+                    if beta:
+                        new = np.sign(new) * np.maximum(np.abs(new) - beta, 0.0)
                 else:
                     new = np.zeros_like(t)
                 rr[ri] = new

@@ -748,6 +748,10 @@ def test_decode2_vs_reference_outputs_and_oracle(name):
     assert np.array_equal(bel_s, O.decode2(rr, bg, zc, ils, n_it, False, True, alpha, False))
     if n_it < nit + 4:
         assert O.parity_ok((bel_s[0] < 0).astype(np.int8), bg, zc, ils)
+    # offset min-sum (extension): |message| = max(alpha * min - beta, 0), against the oracle's restatement of the same rule
+    bel_o = dec.decode2(rr, nit, False, True, alpha, False, beta=0.15)
+    assert np.array_equal(bel_o, O.decode2(rr, bg, zc, ils, nit, False, True, alpha, False, beta=0.15))
+    assert not np.array_equal(bel_o, bel) or not np.abs(rr).any()
     # compatibility switch: the reference's own stop test looks at the first base-graph row only (ldpc.py:841-843)
     bel_f = dec.decode2(rr, nit + 4, False, True, alpha, True, firstRowOnly=True)
     assert np.array_equal(bel_f, O.decode2(rr, bg, zc, ils, nit + 4, False, True, alpha, True, "first_row"))
