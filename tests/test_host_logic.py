@@ -107,3 +107,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "nr_oracle" not in src and "import oracle" not in src and "ref_loader" not in src, f
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The descriptor structs cross the ABI by value / as arrays: sizes and field offsets of the ctypes mirrors
+    (neoradium_b200/_native.py) must equal what a C compiler makes of include/nrldpc.h."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    fields_cfg = ["bg", "zc", "K", "F", "C", "qm", "nl", "ncb", "rv", "reserved", "G"]
+    fields_grp = ["cfg", "in_dtype", "reserved", "llr", "num_tb", "llr_len", "llr_stride", "soft_buffer", "tb_bits",
+                  "tb_bits_stride", "cb_crc_ok", "tb_crc_ok", "iters"]
+    body = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrldpc.h"', 'int main(void) {',
+            'printf("%zu %zu\\n", sizeof(nrldpc_tb_config), sizeof(nrldpc_tb_group));']
+    body += ['printf("%%zu\\n", offsetof(nrldpc_tb_config, %s));' % f for f in fields_cfg]
+    body += ['printf("%%zu\\n", offsetof(nrldpc_tb_group, %s));' % f for f in fields_grp]
+    body += ['return 0; }']
+    src.write_text("\n".join(body))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    sizes, offs = [int(v) for v in out[:2]], [int(v) for v in out[2:]]
+    assert sizes == [ctypes.sizeof(_native.TbConfig), ctypes.sizeof(_native.TbGroup)]
+    want = [getattr(_native.TbConfig, f).offset for f in fields_cfg] + [getattr(_native.TbGroup, f).offset for f in fields_grp]
+    assert offs == want
