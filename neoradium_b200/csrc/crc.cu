@@ -3,6 +3,9 @@
 // LdpcEncoder.doSegmentation (neoradium/ldpc.py:1011-1030) and LdpcDecoder.checkCrcAndMerge (ldpc.py:1610-1619).
 // HBM-bound byte work: a warp per stream segment, 8-byte coalesced traffic, bit-packed table-driven CRC (see below).
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
 
 #include "crc_device.cuh"
 #include "nrldpc_internal.cuh"
@@ -92,6 +95,40 @@ __device__ __forceinline__ uint32_t pack8(uint2 w)
     return ((lo & 0xFu) << 4) | (hi & 0xFu);
 }
 
+// 16 bytes -> 16 bits (first byte in bit 7 of the low byte, ninth byte in bit 7 of the high byte): two words share one
+// multiply -- ((x & m) * 16 + (y & m)) * 0x08040201 has the bits of x in 31..28 and those of y in 27..24, no carries
+__device__ __forceinline__ uint32_t pack16(uint4 w)
+{
+    const uint32_t m = 0x01010101u;
+    const uint32_t a = (((w.x & m) * 16u + (w.y & m)) * 0x08040201u) >> 24;
+    const uint32_t b = (((w.z & m) * 16u + (w.w & m)) * 0x08040201u) >> 16;
+    return a | (b & 0xFF00u);
+}
+
+// `steps` whole warp steps of 512 values (16 per lane): load, copy out (COPY; values masked to their bit with MASK), pack
+template <bool COPY, bool MASK>
+__device__ __forceinline__ void move_pack_steps(const uint4* __restrict__ sp, uint4* __restrict__ dp, unsigned short* pp, int steps,
+                                                bool wantCrc)
+{
+    constexpr uint32_t cm = MASK ? 0x01010101u : 0xFFFFFFFFu;
+    int k = 0;
+    for (; k + 4 <= steps; k += 4) {
+        uint4 w[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) w[u] = __ldcs(sp + (k + u) * 32);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (COPY) __stcs(dp + (k + u) * 32, make_uint4(w[u].x & cm, w[u].y & cm, w[u].z & cm, w[u].w & cm));
+            if (wantCrc) pp[(k + u) * 32] = (unsigned short)pack16(w[u]);
+        }
+    }
+    for (; k < steps; k++) {
+        const uint4 w = __ldcs(sp + k * 32);
+        if (COPY) __stcs(dp + k * 32, make_uint4(w.x & cm, w.y & cm, w.z & cm, w.w & cm));
+        if (wantCrc) pp[k * 32] = (unsigned short)pack16(w);
+    }
+}
+
 __device__ __forceinline__ uint32_t crc_byte_step(uint32_t rem, uint32_t byte, const uint32_t* T, int c, uint32_t mask)
 {
     if (c >= 8) return ((rem << 8) & mask) ^ T[((rem >> (c - 8)) ^ byte) & 0xFFu];
@@ -149,9 +186,24 @@ __global__ void __launch_bounds__(CRC_THREADS)
         //      caller): a lane moves 16 values per step with one 128-bit load / store and packs them into two bytes -- half
         //      the steps of the 8-byte form below (the kernel is bound by instruction issue, not by HBM) ----
         const bool wide = ((reinterpret_cast<uintptr_t>(src + o0) & 15) == 0) && (!dst || ((reinterpret_cast<uintptr_t>(dst + o0) & 15) == 0));
+        int base = 0;   // values of the segment already moved by the check-free loop
+        if (wide) {
+            // whole 512-value warp steps that lie inside the stream, the valid source and the copy: no bounds in the loop,
+            // four 128-bit loads in flight per lane, ~12 instructions per 16 values
+            long long lim = min((long long)nbits, avail - o0);
+            if (dst) lim = min(lim, copyLen - o0);
+            const int nFast = lim > 0 ? (int)(lim >> 9) : 0;
+            const uint4* sp = reinterpret_cast<const uint4*>(src + o0) + lane;
+            uint4* dp = dst ? reinterpret_cast<uint4*>(dst + o0) + lane : nullptr;
+            unsigned short* pp = reinterpret_cast<unsigned short*>(&pk[warp][0]) + lane;
+            if (!dp) move_pack_steps<false, false>(sp, dp, pp, nFast, wantCrc);
+            else if (maskCopy) move_pack_steps<true, true>(sp, dp, pp, nFast, wantCrc);
+            else move_pack_steps<true, false>(sp, dp, pp, nFast, wantCrc);
+            base = nFast << 9;
+        }
         if (wide) {
             constexpr int U2 = (U > 1) ? U / 2 : 1;
-            for (int i0 = lane * 16; i0 < nbits; i0 += 512 * U2) {
+            for (int i0 = base + lane * 16; i0 < nbits; i0 += 512 * U2) {
                 uint4 w[U2];
 #pragma unroll
                 for (int u = 0; u < U2; u++) {
@@ -296,6 +348,54 @@ __global__ void __launch_bounds__(CRC_THREADS)
     }
 }
 
+// GF(2) constants of a call: T (per polynomial), the lane factors (per segment length) and the segment factors (per stream
+// length).  Computing them costs 20-200 us of host time (32 + numSegs square-and-multiply chains of bit-serial products) --
+// more than the kernel itself on a few thousand code blocks -- so the last few combinations are kept.
+struct BsTabEntry {
+    uint32_t poly;
+    int c, numSegs;
+    long long len, seg;
+    unsigned long long stamp;
+    uint32_t T[256], laneFac[32], segFac[CRC_MAX_SEGS];
+};
+void bs_fill_tables(BsArgs& a, long long seg)
+{
+    static BsTabEntry cache[8];
+    static unsigned long long clock = 0;
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    BsTabEntry* e = nullptr;
+    BsTabEntry* victim = &cache[0];
+    for (BsTabEntry& x : cache) {
+        if (x.stamp && x.poly == a.poly && x.c == a.c && x.len == a.len && x.seg == seg && x.numSegs == a.numSegs) { e = &x; break; }
+        if (x.stamp < victim->stamp) victim = &x;
+    }
+    if (!e) {
+        e = victim;
+        e->poly = a.poly; e->c = a.c; e->numSegs = a.numSegs; e->len = a.len; e->seg = seg;
+        const uint32_t mask = (1u << a.c) - 1u;
+        for (int i = 0; i < 256; i++) {   // i(x) * x^c mod g: the 8 bits of i through the bit-serial divider
+            uint32_t rem = 0;
+            for (int b = 7; b >= 0; b--) {
+                const uint32_t fb = ((rem >> (a.c - 1)) & 1u) ^ (((uint32_t)i >> b) & 1u);
+                rem = (rem << 1) & mask;
+                if (fb) rem ^= a.poly;
+            }
+            e->T[i] = rem;
+        }
+        const long long q = seg >> 8;
+        for (int l = 0; l < 32; l++) e->laneFac[l] = host_gf_xpow(8LL * q * (31 - l), a.poly, a.c);
+        for (int g = 0; g < a.numSegs; g++) {
+            const long long end = (a.len < (long long)(g + 1) * seg) ? a.len : (long long)(g + 1) * seg;
+            e->segFac[g] = host_gf_xpow(a.len - end, a.poly, a.c);
+        }
+    }
+    e->stamp = ++clock;
+    memcpy(a.T, e->T, sizeof(a.T));
+    memcpy(a.laneFac, e->laneFac, sizeof(a.laneFac));
+    memcpy(a.segFac, e->segFac, sizeof(uint32_t) * (size_t)a.numSegs);
+}
+
 // segmentation of the streams over warps and launch
 int launch_bitstream(nrldpc_handle* h, BsArgs& a, cudaStream_t st)
 {
@@ -320,24 +420,10 @@ int launch_bitstream(nrldpc_handle* h, BsArgs& a, cudaStream_t st)
         a.acc = (unsigned int*)p;
         a.cnt = a.acc + a.numStreams;
     }
-    const uint32_t mask = (1u << a.c) - 1u;
-    for (int i = 0; i < 256; i++) {   // i(x) * x^c mod g: the 8 bits of i through the bit-serial divider
-        uint32_t rem = 0;
-        for (int b = 7; b >= 0; b--) {
-            const uint32_t fb = ((rem >> (a.c - 1)) & 1u) ^ (((uint32_t)i >> b) & 1u);
-            rem = (rem << 1) & mask;
-            if (fb) rem ^= a.poly;
-        }
-        a.T[i] = rem;
-    }
-    const long long q = seg >> 8;
-    for (int l = 0; l < 32; l++) a.laneFac[l] = host_gf_xpow(8LL * q * (31 - l), a.poly, a.c);
-    for (int g = 0; g < a.numSegs; g++) {
-        const long long end = (a.len < (long long)(g + 1) * seg) ? a.len : (long long)(g + 1) * seg;
-        a.segFac[g] = host_gf_xpow(a.len - end, a.poly, a.c);
-    }
+    bs_fill_tables(a, seg);
     const long long jobs = a.numStreams * a.numSegs;
-    const int grid = (int)max(1LL, min((jobs + CRC_WARPS - 1) / CRC_WARPS, (long long)h->numSMs * 8));
+    static const int perSM = nr_ctas_per_sm(nr_bitstream_kernel<4>, CRC_THREADS, 0);
+    const int grid = (int)max(1LL, min((jobs + CRC_WARPS - 1) / CRC_WARPS, (long long)h->numSMs * perSM));
     // four loads in flight per lane: measured on B200 at 16384 code blocks, U = 1 / 2 / 4 -> 2.9 / 3.1 / 3.8 TB/s (merge)
     nr_bitstream_kernel<4><<<grid, CRC_THREADS, 0, st>>>(a);
     NR_CUDA_CHECK(cudaGetLastError());

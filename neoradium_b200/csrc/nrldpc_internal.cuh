@@ -88,3 +88,16 @@ __host__ __device__ inline NrCrcPoly nr_crc_poly(int id)
         default: return {0xB2B117u, 24};   // 24C
     }
 }
+
+// Resident CTAs per SM of `kern` at this launch shape.  The grid-stride helper kernels are launched as ONE full wave: a grid
+// of "SMs x 8" on a kernel that fits 5 CTAs per SM runs 1.6 waves, the second one 60 % full (ncu launch__waves_per_multiprocessor).
+template <typename K>
+static inline int nr_ctas_per_sm(K kern, int threads, size_t smem)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}

@@ -535,7 +535,7 @@ extern "C" int nrldpc_encode(nrldpc_handle* h, int bg, int zc, const int8_t* cod
         // bit-packed path: vector loads/stores need 16-byte granularity (column length Z is a multiple of 16)
         const int W = (zc + 31) / 32, DW = (2 * zc + 31) / 32 + 2;
         const size_t smem = (size_t)(g.ncore * DW + 4 * W + DW + (g.P - 4) * W) * sizeof(uint32_t);
-        const int grid = (int)min((long long)num_cb, (long long)h->numSMs * 16);
+        const int grid = (int)min((long long)num_cb, (long long)h->numSMs * nr_ctas_per_sm(nr_encode_packed_kernel, ENC_THREADS, smem));
         nr_encode_packed_kernel<<<grid, ENC_THREADS, smem, (cudaStream_t)stream>>>(g, (const signed char*)code_blocks, num_cb,
                                                                                   (signed char*)coded, puncture);
         NR_CUDA_CHECK(cudaGetLastError());
@@ -572,7 +572,7 @@ extern "C" int nrldpc_parity_check_rows(nrldpc_handle* h, int bg, int zc, const 
     if (allRows && zc % 16 == 0 && ((uintptr_t)coded_full & 15) == 0 && !getenv("NRLDPC_ENC_BYTEWISE")) {
         const int W = (zc + 31) / 32, DW = (2 * zc + 31) / 32 + 2;
         const size_t smemP = (size_t)(g.ncore * DW + (g.P - 4) * W) * sizeof(uint32_t);
-        const int gridP = (int)min((long long)num_cb, (long long)h->numSMs * 16);
+        const int gridP = (int)min((long long)num_cb, (long long)h->numSMs * nr_ctas_per_sm(nr_parity_packed_kernel, ENC_THREADS, smemP));
         nr_parity_packed_kernel<<<gridP, ENC_THREADS, smemP, (cudaStream_t)stream>>>(g, (const signed char*)coded_full, num_cb, ok);
         NR_CUDA_CHECK(cudaGetLastError());
         return NRLDPC_OK;
