@@ -126,7 +126,10 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
             a.tmemCols = need;
         }
     }
-    if (multiStatic && !allT && !split) return launch_decode<T>(h, g, a, s, false);   // no such instantiation: generic kernel
+    // (multi-block static kernels exist for all three state layouts: all-TMEM, split and -- low code rates -- tiered)
+    // (measured, all 46 rows of BG1: +4..8 % over the generic kernel at Zc <= 192; CTAs of at most 8 warps -- Zc = 208, 240 -- are
+    // better off with THREE resident generic CTAs: 604 / 675 vs 461 / 528 G edge-updates/s)
+    if (multiStatic && !allT && !split && (nT <= 256 || getenv("NRLDPC_NO_STATIC_MB_TIERED"))) return launch_decode<T>(h, g, a, s, false);
     const int restRows = a.numRows - a.tmemRows;
     size_t budget = (size_t)h->smemPerSM / occ - 1024;
     budget = min(budget, (size_t)h->maxSmemOptin);
@@ -227,6 +230,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         cudaError_t e = cudaErrorNotSupported;
         if (noEs && allt != 0 && z384) e = try_launch(0, 384);
         if (e == cudaErrorNotSupported && noEs && allt != 0) e = try_launch(0, 0);
+        if (e == cudaErrorNotSupported && multiStatic) e = try_launch(0, 0);   // tiered multi-block kernel
         if (e == cudaErrorNotSupported && z384) e = try_launch(1, 384);
         if (e == cudaErrorNotSupported) e = try_launch(1, 0);
         NR_CUDA_CHECK(e);

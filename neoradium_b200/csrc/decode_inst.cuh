@@ -33,6 +33,7 @@ cudaError_t NR_INST_NAME(int allt, int esm, int zs, const void* dg, const void* 
     if (esm != 0 || zs != 0) return cudaErrorNotSupported;
     if (allt == 1) return launch_one(nr_decode_kernel<float, false, BG, 1, 0, 0>, dg, da, grid, nT, smem, s);
     if (allt == 2) return launch_one(nr_decode_kernel<float, false, BG, 2, 0, 0>, dg, da, grid, nT, smem, s);
+    if (allt == 0) return launch_one(nr_decode_kernel<float, false, BG, 0, 0, 0>, dg, da, grid, nT, smem, s);   // tiered state (low rates)
 #elif NR_INST_ES
     if (esm != 1) return cudaErrorNotSupported;
     if (allt == 1 && zs == 384) return launch_one(nr_decode_kernel<float, true, BG, 1, 1, 384>, dg, da, grid, nT, smem, s);

@@ -15,7 +15,7 @@ cudaError_t nr_launch_static_bg2(int allt, int esm, int zs, const void* decGraph
                                  size_t smem, cudaStream_t s);
 cudaError_t nr_launch_static_bg2_es(int allt, int esm, int zs, const void* decGraph, const void* decArgs, unsigned grid, int nT,
                                     size_t smem, cudaStream_t s);
-// several code blocks per CTA (lifting sizes below 224 and those that are no multiple of 32): allt 1 | 2, esm 0, zs 0 only
+// several code blocks per CTA (lifting sizes below 224 and those that are no multiple of 32): allt 0 | 1 | 2, esm 0, zs 0 only
 cudaError_t nr_launch_static_bg1_mb(int allt, int esm, int zs, const void* decGraph, const void* decArgs, unsigned grid, int nT,
                                     size_t smem, cudaStream_t s);
 cudaError_t nr_launch_static_bg2_mb(int allt, int esm, int zs, const void* decGraph, const void* decArgs, unsigned grid, int nT,

@@ -12,6 +12,10 @@ res = {}
 for bg, n, k, edges in ((1, 68, 22, 316), (2, 52, 10, 197)):
     for zc in [int(v) for v in os.environ.get('ZCS', '384,352,320,256,240,208,192,176,128,96,64,32,16,8').split(',')]:
         numCb = max(2048, min(65536, (1 << 24) // (n * zc)))
+        # WAVES=w: at least w full waves of CTAs (3 per SM at most, 384 // zc blocks each): the steady-state rate; without it the
+        # small lifting sizes run 1-3 waves and the figure is mostly the partly filled last one
+        waves = int(os.environ.get('WAVES', '0'))
+        if waves: numCb = max(numCb, waves * 148 * 3 * max(1, 384 // zc))
         f64 = os.environ.get('DT', 'f32') == 'f64'   # DT=f64: the float64 instantiation (the drop-in default precision)
         x = torch.randn((numCb, (n - 2) * zc), device='cuda', dtype=torch.float64 if f64 else torch.float32) * 2 + 1.5
         rows = int(os.environ.get('ROWS', '0'))
