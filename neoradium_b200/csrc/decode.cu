@@ -28,19 +28,39 @@
 
 namespace {
 
-// last column (punctured frame) holding a non-zero LLR, max over the batch -> numRows for mode A
+// last position (punctured frame) holding a non-zero LLR, max over the batch -> numRows for mode A.  A CTA walks whole blocks
+// from their END in chunks of 1024 values (coalesced 4/8-byte loads, four per thread in flight) and leaves a block at the first
+// chunk with a non-zero value or when it reaches the best position any block has reported so far: the pass reads the zero tail
+// of the batch once (nothing at all when the last column is in use) instead of every value with a 64-bit division each.
 template <typename TIn>
-__global__ void nr_last_nonzero_kernel(const TIn* llr, long long numCb, long long stride, int len, int Z, int* lastCol)
+__global__ void __launch_bounds__(256) nr_last_nonzero_kernel(const TIn* __restrict__ llr, long long numCb, long long stride, int len, int* lastPos)
 {
-    int best = -1;
-    const long long total = numCb * (long long)len;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long cb = i / len;
-        const int n = (int)(i - cb * len);
-        if (llr[cb * stride + n] != (TIn)0) best = max(best, n / Z);
+    constexpr int V = 4, CH = 256 * V;
+    __shared__ int loSh;
+    for (long long cb = blockIdx.x; cb < numCb; cb += gridDim.x) {
+        const TIn* __restrict__ p = llr + cb * stride;
+        if (threadIdx.x == 0) loSh = *reinterpret_cast<volatile int*>(lastPos) + 1;   // positions below the current best cannot raise it
+        __syncthreads();
+        const int lo = loSh;   // one value for the whole CTA: the loop below holds barriers
+        for (int hi = len; hi > lo; hi -= CH) {
+            int best = -1;
+            TIn v[V];
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                const int n = hi - 1 - (int)threadIdx.x - k * 256;
+                v[k] = (n >= lo) ? p[n] : (TIn)0;
+            }
+#pragma unroll
+            for (int k = 0; k < V; k++)
+                if (v[k] != (TIn)0) best = max(best, hi - 1 - (int)threadIdx.x - k * 256);
+            if (__syncthreads_or(best >= 0)) {
+                for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(lastPos, best);
+                break;
+            }
+        }
+        __syncthreads();   // the atomicMax of this block is issued before the next block reads the bound
     }
-    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best >= 0) atomicMax(lastCol, best);
 }
 
 template <typename T>
@@ -300,17 +320,17 @@ extern "C" int nrldpc_decode(nrldpc_handle* h, int bg, int zc, int in_dtype, int
         NR_CUDA_CHECK(cudaMemcpyAsync(d, &init, sizeof(int), cudaMemcpyHostToDevice, s));
         const int len = in_cols * zc;
         if (len > 0) {
-            const long long total = num_cb * (long long)len;
-            const int blocks = (int)min((long long)h->numSMs * 8, (total + 255) / 256);
+            const int blocks = (int)min((long long)h->numSMs * 8, (long long)num_cb);
             if (in_dtype == NRLDPC_F32)
-                nr_last_nonzero_kernel<float><<<blocks, 256, 0, s>>>((const float*)llr, num_cb, llr_stride, len, zc, d);
+                nr_last_nonzero_kernel<float><<<blocks, 256, 0, s>>>((const float*)llr, num_cb, llr_stride, len, d);
             else
-                nr_last_nonzero_kernel<double><<<blocks, 256, 0, s>>>((const double*)llr, num_cb, llr_stride, len, zc, d);
+                nr_last_nonzero_kernel<double><<<blocks, 256, 0, s>>>((const double*)llr, num_cb, llr_stride, len, d);
             NR_CUDA_CHECK(cudaGetLastError());
         }
-        int last = -1;
+        int last = -1;   // position, then column
         NR_CUDA_CHECK(cudaMemcpyAsync(&last, d, sizeof(int), cudaMemcpyDeviceToHost, s));
         NR_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (last >= 0) last /= zc;
         const int lastFull = last + 2;                     // un-punctured column index
         int rows = lastFull - g.ksys + 1;                  // row owning that extension column
         a.numRows = max(4, min(g.P, rows));
