@@ -46,7 +46,10 @@ enum { NRLDPC_F32 = 0, NRLDPC_F64 = 1, NRLDPC_F16 = 2 };
 /* decoder flags */
 enum {
     NRLDPC_DEC_EARLY_STOP = 1,  /* extension: stop a code block once all parity checks hold after a full iteration */
-    NRLDPC_DEC_ALL_ROWS = 2     /* disable the (exact) skipping of extension rows whose parity LLRs are all zero */
+    NRLDPC_DEC_ALL_ROWS = 2,    /* disable the (exact) skipping of extension rows whose parity LLRs are all zero */
+    NRLDPC_DEC_ES_AUTO = 4      /* with NRLDPC_DEC_EARLY_STOP: the first tested iteration follows the previous launch on this handle
+                                 * (one less than the smallest iteration count any of its blocks needed; never below ES_FROM):
+                                 * a syndrome test costs ~15 % of an iteration and is wasted before the first block converges */
 };
 /* with NRLDPC_DEC_EARLY_STOP: bits 8..15 of `flags` hold the first iteration (1-based) after which the syndrome is tested;
  * 0 or 1 = after every iteration.  A block then runs at least that many iterations (results per returned iteration count

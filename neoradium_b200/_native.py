@@ -25,12 +25,19 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM = 0, 1, 2, 3
 CRC_IDS = {"6": 0, "11": 1, "16": 2, "24A": 3, "24B": 4, "24C": 5}
 F32, F64, F16 = 0, 1, 2
-DEC_EARLY_STOP, DEC_ALL_ROWS = 1, 2
+DEC_EARLY_STOP, DEC_ALL_ROWS, DEC_ES_AUTO = 1, 2, 4
 
 
 def dec_flags(early_stop, es_from=1):
-    """decoder flags word: NRLDPC_DEC_EARLY_STOP | NRLDPC_DEC_ES_FROM(es_from) (include/nrldpc.h)"""
-    return (DEC_EARLY_STOP | ((max(0, min(255, int(es_from))) & 0xff) << 8)) if early_stop else 0
+    """decoder flags word: NRLDPC_DEC_EARLY_STOP | NRLDPC_DEC_ES_FROM(es_from) (include/nrldpc.h); es_from="auto" sets
+    NRLDPC_DEC_ES_AUTO: the first tested iteration follows the previous launch on the same handle"""
+    if not early_stop:
+        return 0
+    if isinstance(es_from, str):
+        if es_from != "auto":
+            raise ValueError("earlyStopFrom must be an iteration number or 'auto'")
+        return DEC_EARLY_STOP | DEC_ES_AUTO
+    return DEC_EARLY_STOP | ((max(0, min(255, int(es_from))) & 0xff) << 8)
 
 
 class NrldpcError(RuntimeError):

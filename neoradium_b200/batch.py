@@ -56,7 +56,7 @@ class TbBatchCodec:
         self.sumE = int(sum(self.lens))
         self.precision = precision
         self.earlyStop = earlyStop
-        self.earlyStopFrom = earlyStopFrom   # first iteration after which the syndrome is tested (extension, default: every one)
+        self.earlyStopFrom = earlyStopFrom   # first iteration after which the syndrome is tested (extension, default: every one; 'auto': follows the previous launch of this handle -- use ownHandle=True)
         self.device = device if device is not None else _dev.device()
         self.cfg = _native.TbConfig(bg=self.bg, zc=self.Zc, K=self.K, F=self.F, C=self.C, qm=self.qm, nl=self.nl,
                                     ncb=self.ncb, rv=self.rv, reserved=0, G=self.G)

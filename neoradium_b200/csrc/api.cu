@@ -114,6 +114,10 @@ extern "C" int nrldpc_create(int device, nrldpc_handle** out)
     e = cudaMalloc(&h->workCounter, 16 * sizeof(unsigned int));
     if (e != cudaSuccess) { free(h); nr_set_error("cudaMalloc failed: %s", cudaGetErrorString(e)); return NRLDPC_ERR_CUDA; }
     cudaMemset(h->workCounter, 0, 16 * sizeof(unsigned int));
+    {   // [5]: running minimum of the iteration counts (NRLDPC_DEC_ES_AUTO)
+        const unsigned int big = 0x7fffffffu;
+        cudaMemcpy(h->workCounter + 5, &big, sizeof(big), cudaMemcpyHostToDevice);
+    }
     *out = h;
     return NRLDPC_OK;
 }

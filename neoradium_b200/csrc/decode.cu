@@ -220,6 +220,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     }
     a.scratch = h->scratch;
     a.workCounter = getenv("NRLDPC_NO_DYNQ") ? nullptr : h->workCounter;   // dynamic work queue (decode_kernel.cuh)
+    a.esAuto = (a.workCounter && (a.flags & NRLDPC_DEC_EARLY_STOP) && (a.flags & NRLDPC_DEC_ES_AUTO)) ? h->workCounter + 4 : nullptr;
     NrDecGraph dg;
     build_dec_graph<T>(g, &dg, staticRows);
     auto launch = [&](auto kern) -> cudaError_t {

@@ -276,6 +276,9 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
     // that its latency hides behind a whole code block.  With early termination blocks differ in cost and the queue removes
     // the imbalance of a static stride; with a fixed iteration count it degenerates to the same assignment.
     const long long numGroups = (a.numCb + cbPerCta - 1) / cbPerCta;
+    // first iteration (1-based) after which the syndrome is tested: the flags' value, raised by the hint of the previous launch
+    int esFrom = (a.flags >> 8) & 0xff;
+    if (a.esAuto) esFrom = max(esFrom, (int)*reinterpret_cast<volatile unsigned int*>(a.esAuto));
     __shared__ long long nextGrpSh;
     const bool dynQ = a.workCounter != nullptr;
     bool firstGroup = true;
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
             }
             if (!cbDone) itersDone = it + 1;
             if constexpr (SBG != 0) {
-                if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= ((a.flags >> 8) & 0xff)) {
+                if (ESM != 0 && (a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= esFrom) {
                     // Syndrome of the hard decisions after a COMPLETE iteration, bit-packed.  (1) Every warp ballots the sign of
                     // its 32 positions of each core column (stored twice, so a circulant shift is one funnel shift of two
                     // neighbouring words) and of each scheduled extension column (read back from the row state: the row loop
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
                     if (!anyBad) break;
                 }
             } else
-            if ((a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= ((a.flags >> 8) & 0xff)) {
+            if ((a.flags & NRLDPC_DEC_EARLY_STOP) && it + 1 >= esFrom) {
                 // syndrome of the hard decisions after a COMPLETE iteration over the scheduled rows (skipped rows are
                 // satisfied by construction: their parity bit is the parity of the rest)
                 uint32_t bad = 0;
@@ -612,6 +615,7 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
         // -------------------------------------------------------------------------------------------------------
         if (active) {
             if (a.iters && m == 0) a.iters[cb] = itersDone;
+            if (a.esAuto && m == 0) atomicMin(a.esAuto + 1, (unsigned int)itersDone);
             const int outCore = min(a.outCols, ncore);
             if (a.bits) {
                 signed char* o = a.bits + cb * a.bitsStride;
@@ -734,6 +738,10 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
         if (atomicAdd(a.workCounter + 2, 1u) == gridDim.x - 1) {
             a.workCounter[0] = 0u;
             a.workCounter[2] = 0u;
+            if (a.esAuto) {   // every block of this launch has reported: next launch tests from (smallest count - 1)
+                const unsigned int mn = atomicExch(a.esAuto + 1, 0x7fffffffu);
+                a.esAuto[0] = (mn == 0x7fffffffu || mn < 2u) ? 0u : mn - 1u;
+            }
             __threadfence();
         }
     }

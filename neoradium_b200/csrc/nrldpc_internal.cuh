@@ -29,7 +29,7 @@ struct nrldpc_handle {
     int maxSmemOptin;
     void* scratch;          // decoder overflow state (rows that do not fit shared memory), grown on demand
     size_t scratchBytes;
-    unsigned int* workCounter;  // device words: [0] dynamic scheduling counter, [1] last-non-zero-column scan
+    unsigned int* workCounter;  // device words: [0] dynamic scheduling counter, [1] last-non-zero-column scan, [4] / [5] NRLDPC_DEC_ES_AUTO hint / running minimum,
     void* tmp;              // small per-call temporaries (per-code-block CRC partials), grown on demand
     size_t tmpBytes;
     void* tmp2;             // second temporary (multi-segment CRC accumulators; may be live together with `tmp`)

@@ -11,7 +11,9 @@ Extensions (all opt-in, defaults reproduce the reference):
   * ``LdpcDecoder.decodeLLRs(llrs, txBlockSize, numIter, harq=None)``: the fused chain of harq.py:165-173 in one
     kernel, for one transport block or a batch ([numTb, G]) of equally configured ones
   * ``earlyStop``  stop a code block once all parity checks hold (the reference always runs numIter iterations);
-    ``earlyStopFrom=k`` tests the syndrome from iteration k on (a block runs at least k iterations)
+    ``earlyStopFrom=k`` tests the syndrome from iteration k on (a block runs at least k iterations);
+    ``earlyStopFrom='auto'`` lets every launch start the tests one iteration before the first block of the previous
+    launch on the same handle converged (a test costs ~15 % of an iteration and is wasted before that point)
 Deliberate deviations ("do not copy"): the base graph is re-derived whenever (Zc, iLS) change
 (the reference caches a stale one, ldpc.py:777) and ``isValidCodedBlock`` checks all rows (ldpc.py:841-843 returns
 after the first).

@@ -19,7 +19,7 @@ ap.add_argument("--es", action="store_true")
 ap.add_argument("--snr", type=float, default=9.0)
 ap.add_argument("--rate", type=float, default=0.6)
 ap.add_argument("--tag", default="")
-ap.add_argument("--es-from", type=int, default=1)
+ap.add_argument("--es-from", default="1")   # iteration number or "auto"
 args = ap.parse_args()
 C = 16
 A = 8424 * C - 24
@@ -27,7 +27,7 @@ E = int(round(8424 / args.rate / 4)) * 4
 G = E * C
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
-mk = lambda own: TbBatchCodec(1, "16QAM", A, G, precision="fp32", device=dev, ownHandle=own, earlyStop=args.es, earlyStopFrom=args.es_from)
+mk = lambda own: TbBatchCodec(1, "16QAM", A, G, precision="fp32", device=dev, ownHandle=own, earlyStop=args.es, earlyStopFrom=(args.es_from if args.es_from == "auto" else int(args.es_from)))
 codec = mk(False)
 gen = torch.Generator(device=dev)
 gen.manual_seed(1)

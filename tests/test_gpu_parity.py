@@ -325,6 +325,31 @@ def test_early_stop_parity_protocol():
             for r in range(2):
                 hard = (OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, int(it2[t * 2 + r]), np.float32) < 0).astype(np.int8)
                 assert np.array_equal(tb2[t, r * codec.per:(r + 1) * codec.per], hard[0, :codec.per])
+    # earlyStopFrom = 'auto' (NRLDPC_DEC_ES_AUTO): the first launch on a handle tests from iteration 1, every later one from
+    # (smallest iteration count of the previous launch - 1); static and generic kernels, same protocol as above
+    for generic in (False, True):
+        if generic:
+            os.environ["NRLDPC_NO_STATIC_ROWS"] = "1"
+        try:
+            c3 = TbBatchCodec(bg, '16QAM', A, g, precision='fp32', earlyStop=True, earlyStopFrom='auto', ownHandle=True)
+            o1 = c3.decode(llr, 12)
+            i1 = o1["iters"].cpu().numpy().reshape(-1)
+            tb1 = o1["tb"].cpu().numpy()
+            o2 = c3.decode(llr, 12)
+            i2 = o2["iters"].cpu().numpy().reshape(-1)
+            tb3 = o2["tb"].cpu().numpy()
+            o3 = c3.decode(llr, 12)
+            i3 = o3["iters"].cpu().numpy().reshape(-1)
+        finally:
+            os.environ.pop("NRLDPC_NO_STATIC_ROWS", None)
+        assert np.array_equal(i1, iters) and np.array_equal(tb1, tb_h)
+        k = max(1, int(iters.min()) - 1)
+        assert np.array_equal(i2, np.maximum(iters, k)) and np.array_equal(i3, i2)
+        for t in range(numTb):
+            rr, _, p = O.rate_recover(llr_h[t], A, bg, 4, dtype=np.float32)
+            for r in range(2):
+                hard = (OC.decode_beliefs(rr[r:r + 1], bg, 384, 1, int(i2[t * 2 + r]), np.float32) < 0).astype(np.int8)
+                assert np.array_equal(tb3[t, r * codec.per:(r + 1) * codec.per], hard[0, :codec.per])
 
 
 @pytest.mark.parametrize("bg,A,mod,rate,numTb", [(2, 500, 'QPSK', 0.3, 23), (1, 600, '16QAM', 0.5, 40), (2, 24, 'QPSK', 0.25, 130),
