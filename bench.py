@@ -550,7 +550,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world, tbs),
             "e2e": {"value": e2es_val, "unit": UNIT, "h2d_bytes_per_step": h2d_sym, "d2h_bytes_per_step": d2h,
                     "api": "LdpcDecoder.decodeSymbolsAsync(pinned host complex64 equalised symbols, noiseVar, out=pinned host buffers), "
-                           "%d calls in flight: per call a 2-chunk pipeline H2D -> max-log demapper (nrldpc_demap_maxlog, fp32 LLRs) -> "
+                           "%d calls in flight: per call a 2-chunk pipeline H2D -> nrldpc_decode_tb_symbols (max-log demapper inside the decoder's load phase, fp32 LLRs) -> "
                            "fused rate-recovery/decode/CRC -> D2H; every result is read back on the host inside the timed region" % NF,
                     "calls_in_flight": NF,
                     "input": "what PDSCH.getLLRsFromGrid hands to Modem.getLLRsFromSymbols (pdsch.py:935-1000): 8 bytes per symbol = "

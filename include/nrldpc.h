@@ -206,6 +206,19 @@ int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype
                      int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok,
                      uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream);
 
+/* The same chain fed with the EQUALISED SYMBOLS of the codewords instead of their LLRs: what PDSCH.getLLRsFromGrid hands to
+ * Modem.getLLRsFromSymbols (pdsch.py:935-1000, modulation.py:159-204) in front of HarqCW.decodeLLRs (harq.py:165-173).
+ *   symbols    [num_tb, num_sym] complex64 as (re, im) float pairs, pitch sym_stride symbols; num_sym * qm = the LLRs of a
+ *              transport block (G'); noise_var > 0 is the demapper's noise variance
+ * Max-log demapping happens inside the decoder's load phase (no LLR buffer in HBM, no demapper launch) for the lifting sizes
+ * that run one code block per CTA without repetition; every other configuration demaps into a scratch buffer of the handle
+ * first.  Either way the LLRs are, value for value, those of nrldpc_demap_maxlog(F32 -> F32) and the result equals
+ * nrldpc_decode_tb(F32, F32) on them.  fp32 compute, no soft buffer (HARQ combining takes the LLR entry point). */
+int nrldpc_decode_tb_symbols(nrldpc_handle* h, const nrldpc_tb_config* cfg, const float* symbols, int64_t num_tb,
+                             int64_t num_sym, int64_t sym_stride, double noise_var, int num_iter, int flags,
+                             int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok, uint8_t* tb_crc_ok,
+                             int32_t* iters, nrldpc_stream stream);
+
 /* Mixed-configuration batch in ONE call (BASELINE configs[2]: a PDSCH slot whose codewords differ in base graph, lifting
  * size, modulation, layers, redundancy version -- the per-codeword loop of HarqProcess.decodeLLRs, harq.py:331-347, over
  * HarqCW.decodeLLRs, harq.py:165-173).  `groups` is a HOST array of descriptors, one per set of equally configured transport

@@ -148,6 +148,7 @@ SIGNATURES = {
                                      _i32, _vp, _vp, _vp, _vp]),
     "nrldpc_decode_tb": (_i32, [_vp, _cfgp, _i32, _i32, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp,
                                 _vp, _vp, _vp]),
+    "nrldpc_decode_tb_symbols": (_i32, [_vp, _cfgp, _vp, _i64, _i64, _i64, ctypes.c_double, _i32, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
     "nrldpc_decode_tb_groups": (_i32, [_vp, ctypes.POINTER(TbGroup), _i32, _i32, _i32, _i32, _vp]),
     "nrldpc_check_crc_and_merge": (_i32, [_vp, _cfgp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "nrldpc_accumulate_counters": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),

@@ -127,6 +127,23 @@ class TbBatchCodec:
             _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']), _dev.ptr(out['iters']), _dev.stream_ptr()))
         return out
 
+    def decode_symbols(self, symbols, noiseVar, numIter, out=None):
+        """symbols: complex64 [numTb, >= G'/qm] DEVICE tensor of equalised symbols (row pitch = stride(0)) -> the dict of
+        ``decode``.  Max-log demapping (Modem.getLLRsFromSymbols, modulation.py:159-204) runs inside the decoder's load phase
+        where the library has a fused form (one code block per CTA, no repetition) and as a separate pass into a scratch
+        buffer otherwise; the LLRs -- hence every output -- equal ``decode(demap(symbols))`` in fp32 either way."""
+        assert symbols.dtype == torch.complex64 and symbols.dim() == 2 and symbols.stride(1) == 1
+        assert self.precision == 'fp32', "symbol input runs the fp32 chain"
+        numTb = symbols.shape[0]
+        if out is None:
+            out = self.alloc_outputs(numTb)
+        flags = _native.dec_flags(self.earlyStop, self.earlyStopFrom)
+        _native.check(_native.lib().nrldpc_decode_tb_symbols(
+            self._h, self.cfg, _dev.ptr(symbols), numTb, symbols.shape[1], symbols.stride(0), float(noiseVar), int(numIter),
+            flags, _dev.ptr(out['tb']), self.C * self.per, _dev.ptr(out['cbOk']), _dev.ptr(out['tbOk']),
+            _dev.ptr(out['iters']), _dev.stream_ptr()))
+        return out
+
     # ------------------------------------------------------------------------------------------------------------------
     def decode_host(self, llr_host, numIter, out=None, chunks=None, wait=True, slot=0, noiseVar=None):
         """Host-buffer entry point: llr_host is a float32|float64|float16 [numTb, G'] HOST array (NumPy array or CPU torch
@@ -169,7 +186,7 @@ class TbBatchCodec:
                       din=[torch.empty((bounds[i + 1] - bounds[i], Gp), dtype=x.dtype, device=self.device)
                            for i in range(chunks)],
                       dllr=[torch.empty((bounds[i + 1] - bounds[i], (Gp // 2) * self.qm), dtype=torch.float32, device=self.device)
-                            for i in range(chunks)] if symbols else None,
+                            for i in range(chunks)] if (symbols and self.precision != 'fp32') else None,
                       dout=[self.alloc_outputs(bounds[i + 1] - bounds[i]) for i in range(chunks)])
             self._pipe[slot] = st
         if out is None:
@@ -191,7 +208,10 @@ class TbBatchCodec:
                 ev_in.record()
             with torch.cuda.stream(st['comp']):
                 st['comp'].wait_event(ev_in)
-                if symbols:
+                if symbols and self.precision == 'fp32':   # demapper fused into the decoder's load phase (nrldpc_decode_tb_symbols)
+                    self.decode_symbols(torch.view_as_complex(st['din'][i].view(hi - lo, Gp // 2, 2)), noiseVar, numIter,
+                                        out=st['dout'][i])
+                elif symbols:
                     _native.check(_native.lib().nrldpc_demap_maxlog(
                         self._h, self.qm, _native.F32, _dev.ptr(st['din'][i]), (hi - lo) * (Gp // 2), float(noiseVar),
                         _native.F32, _dev.ptr(st['dllr'][i]), _dev.stream_ptr()))

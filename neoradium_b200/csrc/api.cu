@@ -140,6 +140,7 @@ extern "C" int nrldpc_destroy(nrldpc_handle* h)
     if (h->tbAcc) cudaFree(h->tbAcc);
     if (h->tbFacDev) cudaFree(h->tbFacDev);
     if (h->workCounter) cudaFree(h->workCounter);
+    if (h->symLlr) cudaFree(h->symLlr);
     free(h);
     return NRLDPC_OK;
 }

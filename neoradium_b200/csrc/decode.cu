@@ -28,6 +28,8 @@
 
 namespace {
 
+constexpr int NR_DEC_UNSUPPORTED = -1000;   // internal: this launch shape cannot take the requested input form (never leaves the library)
+
 // last position (punctured frame) holding a non-zero LLR, max over the batch -> numRows for mode A.  A CTA walks whole blocks
 // from their END in chunks of 1024 values (coalesced 4/8-byte loads, four per thread in flight) and leaves a block at the first
 // chunk with a non-zero value or when it reaches the best position any block has reported so far: the pass reads the zero tail
@@ -197,14 +199,17 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     }
     if (staticRows && oneCb && a.rm && !a.softBuf && !a.inF64 && !h->noStage && (reinterpret_cast<uintptr_t>(a.llr) & 15) == 0) {
         const int Emax = a.E0 + ((a.nShort < a.C) ? a.fStep : 0);
-        const int es = a.inF16 ? 2 : 4, epv = 16 / es;
-        const size_t need = ((size_t)((Emax + 2 * (epv - 1)) & ~(epv - 1)) * es + 15) & ~(size_t)15;
+        const int es = a.inSym ? 8 : (a.inF16 ? 2 : 4), epv = 16 / es;   // symbols: Emax / qm complex64 values
+        const int elems = a.inSym ? Emax / a.qm : Emax;
+        const size_t need = ((size_t)((elems + 2 * (epv - 1)) & ~(epv - 1)) * es + 15) & ~(size_t)15;
         const size_t used = rBytes + (size_t)smemRows * rowBytes + miscBytes;
         // half-precision streams are consumed from the staging buffer only by the no-repetition load (E <= Ncb - F): a launch
         // that holds a longer block would leave its copy unconsumed and the barrier phase out of step, so it does not stage
-        const bool f16Wrap = a.inF16 && Emax > a.ncb - a.F;
+        const bool f16Wrap = (a.inF16 || a.inSym) && Emax > a.ncb - a.F;
         if (used + need <= budget && need <= (size_t)(1u << 19) && !f16Wrap) a.stageFloats = (int)(need / sizeof(float));
     }
+    // symbol input is consumed by the staged load of the one-block static fp32 kernels only: the caller demaps first otherwise
+    if (a.inSym && !(a.stageFloats > 0 && staticRows && oneCb && sizeof(T) == 4)) return NR_DEC_UNSUPPORTED;
     const size_t smem = rBytes + (size_t)smemRows * rowBytes + miscBytes + (size_t)a.stageFloats * sizeof(float);
     const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
     int perSM = (int)((size_t)h->smemPerSM / (smem + 1024));
@@ -382,10 +387,12 @@ extern "C" int nrldpc_decode2_offset(nrldpc_handle* h, int bg, int zc, int in_dt
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, (cudaStream_t)stream);
 }
 
-extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,
-                                const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride,
-                                void* soft_buffer, int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride,
-                                uint8_t* cb_crc_ok, uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream)
+// nrldpc_decode_tb; noise_var > 0: `llr` holds complex64 symbols (llr_len / llr_stride still count LLRs), NR_DEC_UNSUPPORTED when
+// this configuration has no fused symbol path
+static int decode_tb_impl(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,
+                          const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride,
+                          void* soft_buffer, int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride,
+                          uint8_t* cb_crc_ok, uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream, double noise_var)
 {
     if (!h || !cfg) { nr_set_error("decode_tb: null argument"); return NRLDPC_ERR_ARG; }
     NrGraph g;
@@ -406,6 +413,8 @@ extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, i
     a.llrStride = llr_stride;
     a.llrLen = llr_len;
     a.rm = 1;
+    a.inSym = noise_var > 0.0 ? 1 : 0;
+    a.invN0 = noise_var > 0.0 ? 1.0 / noise_var : 0.0;   // the demapper's own expression (linksim.cu)
     a.K = cfg->K; a.F = cfg->F; a.C = cfg->C; a.qm = cfg->qm; a.ncb = cfg->ncb;
     nr_tb_split(cfg, N, &a.E0, &a.nShort, &a.fStep, &a.k0);
     a.softBuf = soft_buffer;
@@ -472,6 +481,55 @@ extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, i
         a.numRows = max(4, min(g.P, lastFull - g.ksys + 1));
     }
     return dispatch_decode(h, g, a, in_dtype, compute_dtype, s);
+}
+
+extern "C" int nrldpc_decode_tb(nrldpc_handle* h, const nrldpc_tb_config* cfg, int in_dtype, int compute_dtype,
+                                const void* llr, int64_t num_tb, int64_t llr_len, int64_t llr_stride,
+                                void* soft_buffer, int num_iter, int flags, int8_t* tb_bits, int64_t tb_bits_stride,
+                                uint8_t* cb_crc_ok, uint8_t* tb_crc_ok, int32_t* iters, nrldpc_stream stream)
+{
+    return decode_tb_impl(h, cfg, in_dtype, compute_dtype, llr, num_tb, llr_len, llr_stride, soft_buffer, num_iter, flags, tb_bits,
+                          tb_bits_stride, cb_crc_ok, tb_crc_ok, iters, stream, 0.0);
+}
+
+extern "C" int nrldpc_decode_tb_symbols(nrldpc_handle* h, const nrldpc_tb_config* cfg, const float* symbols, int64_t num_tb,
+                                        int64_t num_sym, int64_t sym_stride, double noise_var, int num_iter, int flags,
+                                        int8_t* tb_bits, int64_t tb_bits_stride, uint8_t* cb_crc_ok, uint8_t* tb_crc_ok,
+                                        int32_t* iters, nrldpc_stream stream)
+{
+    if (!h || !cfg || !symbols) { nr_set_error("decode_tb_symbols: null argument"); return NRLDPC_ERR_ARG; }
+    if (num_tb <= 0 || num_sym < 0 || sym_stride < num_sym || !(noise_var > 0.0) || cfg->qm < 1) {
+        nr_set_error("decode_tb_symbols: bad arguments");
+        return NRLDPC_ERR_ARG;
+    }
+    const int64_t llrLen = num_sym * cfg->qm, llrStride = sym_stride * cfg->qm;
+    int rc = NR_DEC_UNSUPPORTED;
+    if (!getenv("NRLDPC_NO_FUSED_DEMAP"))
+        rc = decode_tb_impl(h, cfg, NRLDPC_F32, NRLDPC_F32, symbols, num_tb, llrLen, llrStride, nullptr, num_iter, flags, tb_bits,
+                            tb_bits_stride, cb_crc_ok, tb_crc_ok, iters, stream, noise_var);
+    if (rc != NR_DEC_UNSUPPORTED) return rc;
+    // no fused form for this configuration (several blocks per CTA, repetition, no staging room): demap into a scratch buffer
+    // of the handle, then the ordinary fused chain -- the same LLRs either way
+    const size_t bytes = (size_t)num_tb * (size_t)llrLen * sizeof(float);
+    if (bytes > h->symLlrBytes) {
+        if (h->symLlr) NR_CUDA_CHECK(cudaFree(h->symLlr));
+        h->symLlr = nullptr;
+        h->symLlrBytes = 0;
+        NR_CUDA_CHECK(cudaMalloc(&h->symLlr, bytes));
+        h->symLlrBytes = bytes;
+    }
+    if (sym_stride == num_sym) {
+        rc = nrldpc_demap_maxlog(h, cfg->qm, NRLDPC_F32, symbols, num_tb * num_sym, noise_var, NRLDPC_F32, h->symLlr, stream);
+        if (rc) return rc;
+    } else {
+        for (int64_t t = 0; t < num_tb; t++) {
+            rc = nrldpc_demap_maxlog(h, cfg->qm, NRLDPC_F32, symbols + 2 * t * sym_stride, num_sym, noise_var, NRLDPC_F32,
+                                     (float*)h->symLlr + t * llrLen, stream);
+            if (rc) return rc;
+        }
+    }
+    return decode_tb_impl(h, cfg, NRLDPC_F32, NRLDPC_F32, h->symLlr, num_tb, llrLen, llrLen, nullptr, num_iter, flags, tb_bits,
+                          tb_bits_stride, cb_crc_ok, tb_crc_ok, iters, stream, 0.0);
 }
 
 extern "C" int nrldpc_decode_tb_groups(nrldpc_handle* h, const nrldpc_tb_group* groups, int num_groups, int compute_dtype,

@@ -67,6 +67,8 @@ struct DecArgs {
     void* scratch;
     unsigned int* workCounter;
     unsigned int* esAuto;   // NRLDPC_DEC_ES_AUTO: [0] hint for this launch (first tested iteration), [1] running minimum of the iteration counts
+    int inSym;          // fused chain: `llr` holds complex64 equalised SYMBOLS (re, im floats); llrLen / llrStride stay in LLR units
+    double invN0;       // 1 / noise variance of the max-log demapper (inSym)
     // static fp32 kernels: the TMA staging buffer of the fused load phase
     int stageFloats;
     // fused CRC of the static kernels: per-thread factors x^(B (Z-1-m)) mod g for the code-block CRC [0, Z) and the

@@ -5,6 +5,7 @@
 #include "crc_device.cuh"
 #include "decode_common.cuh"
 #include "decode_static.cuh"
+#include "demap_device.cuh"
 
 namespace {
 
@@ -235,6 +236,17 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
         }
     }
 
+    // symbol input (nrldpc_decode_tb_symbols; one-block static fp32 kernels with a staged stream only): the per-axis amplitude
+    // levels of the demapper, the same expression as nr_demap_kernel's
+    constexpr bool SYM = (SBG != 0) && ONE_CB && sizeof(T) == 4;
+    __shared__ double demapLevels[SYM ? 32 : 1];
+    if constexpr (SYM) {
+        if (a.inSym) {
+            const int half = a.qm >> 1;
+            if (a.qm > 1 && tid < (1 << half)) demapLevels[tid] = qam_scale(a.qm) * (double)pam_level((uint32_t)tid, half);
+            __syncthreads();
+        }
+    }
     const bool wantCrc = a.rm && (a.tbBits || a.cbCrcOk || a.tbOk);
     const int Lk = a.K - a.F;                       // code block without fillers
     const int per = (a.C > 1) ? Lk - 24 : Lk;       // payload copied into the merged transport block
@@ -263,6 +275,13 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
         long long xBase, xAvail;
         stream_geom(cbi, E, xBase, xAvail);
         const int n = (int)(xAvail < 0 ? 0 : (xAvail > (long long)E ? (long long)E : xAvail));
+        if (a.inSym) {   // n / qm symbols of 8 bytes from symbol xBase / qm on (E, the offsets and the pitch are multiples of qm)
+            const long long xs = xBase / a.qm;
+            const int headS = (int)(xs & 1), nCopyS = (headS + n / a.qm) & ~1;
+            stage_issue(barStage, (uint32_t)__cvta_generic_to_shared(stage),
+                        reinterpret_cast<const char*>(a.llr) + (xs - headS) * 8, (uint32_t)(nCopyS * 8));
+            return;
+        }
         const int es = a.inF16 ? 2 : 4, epv = 16 / es;   // element size, elements per 16 bytes
         const int head = (int)(xBase & (epv - 1));
         const int nCopy = (head + n) & ~(epv - 1);
@@ -402,8 +421,53 @@ __global__ void __launch_bounds__((WPQ == 2 ? 256 : 384), (sizeof(T) == 4 ? (WPQ
                     }
                 }
             };
+            // staged SYMBOLS: stream element xi = r * qm + b is bit b of symbol r of the block; its LLR is computed here,
+            // value for value as nr_demap_kernel<float, float> would have written it (no LLR buffer, no demapper launch)
+            auto staged_load_sym = [&]() {
+                if constexpr (SYM) {
+                    const int ncb = a.ncb, F = a.F, k0 = a.k0, qm = a.qm;
+                    const long long xs = xBase / qm;
+                    const float2* __restrict__ x = reinterpret_cast<const float2*>(a.llr) + xs;
+                    const int headS = (int)(xs & 1);
+                    const int nCopyS = (headS + xAvailI / qm) & ~1;
+                    mbar_wait(barStage, stagePhase);
+                    stagePhase ^= 1u;
+                    const float2* __restrict__ sp = reinterpret_cast<const float2*>(stage) + headS;
+                    const int nStagedS = nCopyS - headS;
+                    const double invN0 = a.invN0;
+                    int n = m;
+                    for (int col = 2; col < lastCol; col++, n += Z) {
+                        const int nf = n - sysLen;
+                        const bool isFill = (unsigned)nf < (unsigned)F;
+                        int i = n - (nf >= 0 ? F : 0) - k0;
+                        i += (i < 0) ? L : 0;
+                        int b = (int)((float)i * rcpEq);
+                        int r = i - b * Eq;
+                        b += (r >= Eq) ? 1 : 0;
+                        r -= (r >= Eq) ? Eq : 0;
+                        b -= (r < 0) ? 1 : 0;
+                        r += (r < 0) ? Eq : 0;
+                        const bool valid = (n < ncb) && !isFill && (i < E) && (r * qm + b < xAvailI);
+                        float2 y = sp[(valid && r < nStagedS) ? r : 0];
+                        if (valid && r >= nStagedS) y = x[r];   // behind the last whole 16 bytes
+                        T v = (T)demap_bit_f32(y.x, y.y, valid ? b : 0, qm, demapLevels, invN0);
+                        v = FP<T>::mn(v, (T)1e10);
+                        v = FP<T>::mx(v, (T)-1e10);
+                        v = FP<T>::add(v, (T)0);
+                        v = valid ? v : ((isFill && n < ncb) ? (T)1e10 : (T)0);
+                        if (col < ncore) {
+                            rcb[col * Z + m] = v;
+                        } else {
+                            RowState<T> st0;
+                            st0.m1s = (T)0; st0.m2s = (T)0; st0.sw = 0; st0.rext = v;
+                            store.store(col - ksys, st0);
+                        }
+                    }
+                }
+            };
             if (useStage && E <= L) {
-                if (a.inF16) staged_load(__half()); else staged_load(float());
+                if (SYM && a.inSym) staged_load_sym();
+                else if (a.inF16) staged_load(__half()); else staged_load(float());
             } else if (a.rm && !a.softBuf && !a.inF64 && !a.inF16 && smallE) {
                 // common case (fp32 stream, no HARQ history): same arithmetic, none of the generic bookkeeping
                 const float* __restrict__ x = reinterpret_cast<const float*>(a.llr) + xBase;

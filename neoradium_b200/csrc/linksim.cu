@@ -13,22 +13,12 @@
 // HBM-bound streaming kernels: a thread owns a group of symbols whose LLRs fill whole 16-byte stores.
 #include <math.h>
 
+#include "demap_device.cuh"
 #include "nrldpc_internal.cuh"
 
 namespace {
 
 constexpr int LS_THREADS = 256;
-
-__host__ __device__ inline double qam_scale(int qm)
-{
-    switch (qm) {
-        case 1: case 2: return 1.0 / sqrt(2.0);
-        case 4: return 1.0 / sqrt(10.0);
-        case 6: return 1.0 / sqrt(42.0);
-        case 8: return 1.0 / sqrt(170.0);
-        default: return 1.0 / sqrt(682.0);
-    }
-}
 
 // integer amplitudes (re, im) of the label `v` (qm bits, b0 = MSB), modulation.py:64-72
 __device__ __forceinline__ void qam_point(uint32_t v, int qm, int& re, int& im)
@@ -42,14 +32,6 @@ __device__ __forceinline__ void qam_point(uint32_t v, int qm, int& re, int& im)
     }
     re *= 1 - 2 * bit(0);
     im *= 1 - 2 * bit(qm > 1 ? 1 : 0);
-}
-
-// amplitude of one axis from its `half` label bits (MSB = the sign bit b0 | b1, then outer .. inner)
-__device__ __forceinline__ int pam_level(uint32_t lab, int half)
-{
-    int a = 1;
-    for (int p = half - 1; p >= 1; p--) a = (1 << (half - p)) - (1 - 2 * (int)((lab >> (half - 1 - p)) & 1u)) * a;
-    return (1 - 2 * (int)((lab >> (half - 1)) & 1u)) * a;
 }
 
 template <typename T>

@@ -30,6 +30,8 @@ struct nrldpc_handle {
     void* scratch;          // decoder overflow state (rows that do not fit shared memory), grown on demand
     size_t scratchBytes;
     unsigned int* workCounter;  // device words: [0] dynamic scheduling counter, [1] last-non-zero-column scan, [4] / [5] NRLDPC_DEC_ES_AUTO hint / running minimum,
+    void* symLlr;           // nrldpc_decode_tb_symbols without a fused form: LLR scratch, grown on demand
+    size_t symLlrBytes;
     void* tmp;              // small per-call temporaries (per-code-block CRC partials), grown on demand
     size_t tmpBytes;
     void* tmp2;             // second temporary (multi-segment CRC accumulators; may be live together with `tmp`)

@@ -147,3 +147,45 @@ def test_symbol_input_host_pipeline_equals_llr_input():
     p1 = dec.decodeSymbolsAsync(sym[3:], n0, A, 8, slot=1)
     a, b = p0.result(), p1.result()
     assert np.array_equal(np.concatenate([a[0], b[0]]), tb_s) and np.array_equal(np.concatenate([a[2], b[2]]), ok_s)
+
+
+def test_fused_symbol_input_equals_demapper_plus_decoder():
+    """nrldpc_decode_tb_symbols (TbBatchCodec.decode_symbols): the demapper inside the decoder's load phase -- and its
+    demap-first fall-back for configurations without a fused form -- gives exactly the outputs of nrldpc_demap_maxlog (fp32 LLRs)
+    followed by nrldpc_decode_tb: one block per CTA at several lifting sizes / modulations / redundancy versions, filler bits,
+    a pitched symbol array, a partly present codeword (fewer symbols than G'/qm), and the fall-back cases (several blocks per
+    CTA, repetition E > Ncb, BPSK)."""
+    import torch
+    from neoradium_b200 import _dev, _native
+    from neoradium_b200.batch import TbBatchCodec
+    from neoradium_b200.modulation import awgn_llr
+    L, h = _native.lib(), _dev.handle()
+    #        bg  mod      A      G      numTb rv  pad  cut
+    cases = [(1, '16QAM', 8424 * 3 - 24, 14040 * 3, 5, 0, 0, 0), (1, '64QAM', 20000, 30000, 4, 2, 6, 0), (1, 'QPSK', 7000, 11000, 3, 3, 0, 0),
+             (1, '256QAM', 8000, 12000, 3, 0, 0, 0), (2, 'QPSK', 3000, 9000, 4, 1, 2, 0), (1, '16QAM', 8424 * 2 - 24, 14040 * 2, 3, 0, 0, 500),
+             (2, 'QPSK', 500, 1668, 7, 0, 0, 0), (1, '16QAM', 600, 1200, 5, 0, 0, 0), (2, 'QPSK', 100, 2000, 3, 0, 0, 0), (1, 'BPSK', 640, 1280, 2, 0, 0, 0)]
+    for bg, mod, A, G, numTb, rv, pad, cut in cases:
+        qm = {'BPSK': 1, 'QPSK': 2, '16QAM': 4, '64QAM': 6, '256QAM': 8}[mod]
+        G = (G // qm) * qm
+        codec = TbBatchCodec(bg, mod, A, G, 1, 0, rv, 'fp32', ownHandle=True)
+        rm = codec.encode(codec.random_payload(numTb, 11))
+        nsym = G // qm
+        # symbols = hard constellation points + noise, built on the device from the modulator and torch's generator
+        x = torch.empty((numTb, nsym, 2), dtype=torch.float32, device='cuda')
+        _native.check(L.nrldpc_modulate(h, qm, _dev.ptr(rm), numTb * nsym, _native.F32, _dev.ptr(x), _dev.stream_ptr()))
+        gen = torch.Generator(device='cuda'); gen.manual_seed(A)
+        n0 = 10 ** (-{1: 4.0, 2: 6.0, 4: 12.0, 6: 18.0, 8: 24.0}[qm] / 10)   # Es/N0 at which most transport blocks decode
+        y = x + torch.randn(x.shape, device='cuda', generator=gen) * float(np.sqrt(n0 / 2))
+        buf = torch.zeros((numTb, nsym + pad, 2), dtype=torch.float32, device='cuda')
+        buf[:, :nsym] = y
+        sym = torch.view_as_complex(buf)[:, :nsym - cut]                      # pitch nsym + pad, nsym - cut symbols present
+        llr = torch.empty((numTb, (nsym - cut) * qm), dtype=torch.float32, device='cuda')
+        yc = y[:, :nsym - cut].contiguous()
+        _native.check(L.nrldpc_demap_maxlog(h, qm, _native.F32, _dev.ptr(yc), numTb * (nsym - cut), float(n0), _native.F32, _dev.ptr(llr),
+                                            _dev.stream_ptr()))
+        ref = codec.decode(llr, 6)
+        out = codec.decode_symbols(sym, n0, 6)
+        torch.cuda.synchronize()
+        for k in ('tb', 'cbOk', 'tbOk', 'iters'):
+            assert torch.equal(out[k], ref[k]), (bg, mod, A, k)
+        assert cut or int(ref['tbOk'].sum()) > 0, (bg, mod, A)
