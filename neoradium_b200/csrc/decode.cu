@@ -107,18 +107,30 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // "split" kernels keep both CTAs and know every row's tier at compile time
     // CTAs of at most 8 warps (Zc <= 256; no early termination): THREE per SM, each with 128 Tensor-Memory columns = 16 rows at two
     // warps per lane quadrant; further rows in shared-memory planes when they fit a third of the SM ("w8" instantiations)
-    bool w8 = false, w8AllT = false;
+    bool w8 = false, w8AllT = false, w8Tiered = false, w8Eligible = false;
     if (staticRows && sizeof(T) == 4 && nT <= 256 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && h->decOcc <= 0 && !h->noTmem &&
         !getenv("NRLDPC_NO_W8")) {
         const size_t budget3 = min((size_t)h->smemPerSM / 3 - 1024, (size_t)h->maxSmemOptin);
         w8AllT = a.numRows <= 16;
         w8 = rBytes + miscBytes + (size_t)(w8AllT ? 0 : a.numRows - 16) * rowBytes <= budget3;
+        // low code rates: still three CTAs per SM, the rows beyond Tensor Memory and the planes in the L2 scratch ("w8 tiered")
         if (w8) occ = 3;
+        else w8Eligible = rBytes + miscBytes + 2 * rowBytes <= budget3;
     }
     bool split = w8 && !w8AllT;
     if (!w8 && staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
         const size_t budget2 = min((size_t)h->smemPerSM / 2 - 1024, (size_t)h->maxSmemOptin);
         split = rBytes + miscBytes + (size_t)(a.numRows - 21) * rowBytes <= budget2;
+    }
+    // low code rates on narrow CTAs: when the rows fit neither the three-CTA planes nor the two-CTA split, keep THREE CTAs per SM with
+    // the rows beyond Tensor Memory and the planes in the L2 scratch ("w8 tiered") instead of two tiered CTAs / one all-TMEM CTA
+    if (w8Eligible && !split) {
+        const char* wt = getenv("NRLDPC_W8_TIERED_FROM");
+        const bool wouldBeOne = a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512;
+        if (a.numRows >= (wt ? atoi(wt) : 43) || (wouldBeOne && !getenv("NRLDPC_NO_W8_TIERED_OCC1"))) {
+            w8Tiered = true;
+            occ = 3;
+        }
     }
     if (!w8 && !split && staticRows && h->decOcc <= 0 && occ == 2 && a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512) occ = 1;
     // Tensor Memory rows (ONE_CB kernels): 512 columns per SM shared by the resident CTAs
@@ -127,6 +139,10 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     bool allT = w8 && w8AllT;
     if (w8) {
         a.tmemRows = a.numRows < 16 ? a.numRows : 16;
+        a.tmemCols = 128;
+    } else if (w8Tiered) {
+        const int wpq = ((nT >> 5) + 3) >> 2;   // the kernel's run-time stride (ALLT = 0)
+        a.tmemRows = min(a.numRows, 128 / (wpq * 4));
         a.tmemCols = 128;
     } else if ((oneCb || multiStatic) && !h->noTmem) {
         int cols = 32;
@@ -151,7 +167,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // (multi-block static kernels exist for all three state layouts: all-TMEM, split and -- low code rates -- tiered)
     // (measured, all 46 rows of BG1: +4..8 % over the generic kernel at Zc <= 192; CTAs of at most 8 warps -- Zc = 208, 240 -- are
     // better off with THREE resident generic CTAs: 604 / 675 vs 461 / 528 G edge-updates/s)
-    if (multiStatic && !allT && !split && (nT <= 256 || getenv("NRLDPC_NO_STATIC_MB_TIERED"))) return launch_decode<T>(h, g, a, s, false);
+    if (multiStatic && !allT && !split && !w8Tiered && (nT <= 256 || getenv("NRLDPC_NO_STATIC_MB_TIERED"))) return launch_decode<T>(h, g, a, s, false);
     const int restRows = a.numRows - a.tmemRows;
     size_t budget = (size_t)h->smemPerSM / occ - 1024;
     budget = min(budget, (size_t)h->maxSmemOptin);
@@ -244,7 +260,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         const bool bg1 = g.P == NR_BG1_ROWS;
         // preference order: no early-termination code + compile-time table, no early-termination code, everything
         auto try_launch = [&](int esm, int zs) -> cudaError_t {
-            if (w8) return bg1 ? nr_launch_static_bg1_w8(allt, oneCb ? 1 : 0, &dg, &a, (unsigned)grid, nT, smem, s)
+            if (w8 || w8Tiered) return bg1 ? nr_launch_static_bg1_w8(allt, oneCb ? 1 : 0, &dg, &a, (unsigned)grid, nT, smem, s)
                                : nr_launch_static_bg2_w8(allt, oneCb ? 1 : 0, &dg, &a, (unsigned)grid, nT, smem, s);
             if (multiStatic) return bg1 ? nr_launch_static_bg1_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s)
                                         : nr_launch_static_bg2_mb(allt, esm, zs, &dg, &a, (unsigned)grid, nT, smem, s);

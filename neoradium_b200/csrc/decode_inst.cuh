@@ -22,6 +22,8 @@ cudaError_t NR_INST_NAME(int allt, int oneCb, const void* dg, const void* da, un
     if (oneCb && allt == 2) return launch_one(nr_decode_kernel<float, true, BG, 2, 0, 0, 2>, dg, da, grid, nT, smem, s);
     if (!oneCb && allt == 1) return launch_one(nr_decode_kernel<float, false, BG, 1, 0, 0, 2>, dg, da, grid, nT, smem, s);
     if (!oneCb && allt == 2) return launch_one(nr_decode_kernel<float, false, BG, 2, 0, 0, 2>, dg, da, grid, nT, smem, s);
+    if (oneCb && allt == 0) return launch_one(nr_decode_kernel<float, true, BG, 0, 0, 0, 2>, dg, da, grid, nT, smem, s);    // tiered state
+    if (!oneCb && allt == 0) return launch_one(nr_decode_kernel<float, false, BG, 0, 0, 0, 2>, dg, da, grid, nT, smem, s);
     return cudaErrorNotSupported;
 }
 #else

@@ -254,7 +254,9 @@ def test_decoder_kernel_variants_agree(monkeypatch):
     rng = np.random.default_rng(33)
     knobs = [{}, {"NRLDPC_NO_SPECZ": "1"}, {"NRLDPC_ES_CODE": "1"}, {"NRLDPC_NO_SPLIT": "1"}, {"NRLDPC_NO_SPLIT": "1", "NRLDPC_NO_SPECZ": "1"},
              {"NRLDPC_NO_SPECZ": "1", "NRLDPC_ES_CODE": "1"}]
-    for bg, zc, rows in [(1, 384, 17), (1, 384, 26), (2, 384, 26), (2, 384, 42), (1, 320, 24), (1, 384, 40), (1, 384, 46)]:
+    # (the second line: low code rates on CTAs of at most 8 warps -- three tiered CTAs per SM -- and on multi-block CTAs)
+    for bg, zc, rows in [(1, 384, 17), (1, 384, 26), (2, 384, 26), (2, 384, 42), (1, 320, 24), (1, 384, 40), (1, 384, 46),
+                         (1, 256, 42), (1, 256, 46), (1, 240, 42), (1, 240, 38), (1, 224, 46), (1, 208, 42), (2, 240, 42), (1, 128, 46), (1, 60, 44)]:
         _, n, k = O.bg_dims(bg)
         ils = O.set_index_of(zc)
         C = 3
