@@ -28,6 +28,10 @@
 
 namespace {
 
+// shared memory a resident CTA costs on top of its dynamic allocation: 1 KB reserved by the system + the kernel's static variables
+// (~1.6 KB).  Counting only the 1 KB let the planes of the tiered kernels fill the budget so exactly that the second CTA no longer
+// fitted (BG1 Zc=288, all 46 rows: ONE resident CTA, 328 instead of ~700 G edge-updates/s).
+constexpr size_t kCtaSmemOverhead = 1024 + 2048;
 constexpr int NR_DEC_UNSUPPORTED = -1000;   // internal: this launch shape cannot take the requested input form (never leaves the library)
 
 // last position (punctured frame) holding a non-zero LLR, max over the batch -> numRows for mode A.  A CTA walks whole blocks
@@ -110,7 +114,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     bool w8 = false, w8AllT = false, w8Tiered = false, w8Eligible = false;
     if (staticRows && sizeof(T) == 4 && nT <= 256 && !(a.flags & NRLDPC_DEC_EARLY_STOP) && h->decOcc <= 0 && !h->noTmem &&
         !getenv("NRLDPC_NO_W8")) {
-        const size_t budget3 = min((size_t)h->smemPerSM / 3 - 1024, (size_t)h->maxSmemOptin);
+        const size_t budget3 = min((size_t)h->smemPerSM / 3 - kCtaSmemOverhead, (size_t)h->maxSmemOptin);
         w8AllT = a.numRows <= 16;
         w8 = rBytes + miscBytes + (size_t)(w8AllT ? 0 : a.numRows - 16) * rowBytes <= budget3;
         // low code rates: still three CTAs per SM, the rows beyond Tensor Memory and the planes in the L2 scratch ("w8 tiered")
@@ -119,7 +123,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     }
     bool split = w8 && !w8AllT;
     if (!w8 && staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
-        const size_t budget2 = min((size_t)h->smemPerSM / 2 - 1024, (size_t)h->maxSmemOptin);
+        const size_t budget2 = min((size_t)h->smemPerSM / 2 - kCtaSmemOverhead, (size_t)h->maxSmemOptin);
         split = rBytes + miscBytes + (size_t)(a.numRows - 21) * rowBytes <= budget2;
     }
     // low code rates on narrow CTAs: when the rows fit neither the three-CTA planes nor the two-CTA split, keep THREE CTAs per SM with
@@ -169,7 +173,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     // better off with THREE resident generic CTAs: 604 / 675 vs 461 / 528 G edge-updates/s)
     if (multiStatic && !allT && !split && !w8Tiered && (nT <= 256 || getenv("NRLDPC_NO_STATIC_MB_TIERED"))) return launch_decode<T>(h, g, a, s, false);
     const int restRows = a.numRows - a.tmemRows;
-    size_t budget = (size_t)h->smemPerSM / occ - 1024;
+    size_t budget = (size_t)h->smemPerSM / occ - kCtaSmemOverhead;
     budget = min(budget, (size_t)h->maxSmemOptin);
     if (rBytes + miscBytes > budget) {
         occ = 1;
@@ -228,7 +232,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     if (a.inSym && !(a.stageFloats > 0 && staticRows && oneCb && sizeof(T) == 4)) return NR_DEC_UNSUPPORTED;
     const size_t smem = rBytes + (size_t)smemRows * rowBytes + miscBytes + (size_t)a.stageFloats * sizeof(float);
     const long long numGroups = (a.numCb + a.cbPerCta - 1) / a.cbPerCta;
-    int perSM = (int)((size_t)h->smemPerSM / (smem + 1024));
+    int perSM = (int)((size_t)h->smemPerSM / (smem + kCtaSmemOverhead));
     perSM = max(1, min(min(perSM, 2048 / nT), occ));
     long long grid = min(numGroups, (long long)h->numSMs * perSM);
     const size_t needScratch = (size_t)grid * (size_t)(restRows - smemRows) * rowBytes;
@@ -271,7 +275,7 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         };
         cudaError_t e = cudaErrorNotSupported;
         if (noEs && allt != 0 && z384) e = try_launch(0, 384);
-        if (e == cudaErrorNotSupported && noEs && allt != 0) e = try_launch(0, 0);
+        if (e == cudaErrorNotSupported && noEs && (allt != 0 || !getenv("NRLDPC_TIERED_ES_CODE"))) e = try_launch(0, 0);
         if (e == cudaErrorNotSupported && multiStatic) e = try_launch(0, 0);   // tiered multi-block kernel
         if (e == cudaErrorNotSupported && z384) e = try_launch(1, 384);
         if (e == cudaErrorNotSupported) e = try_launch(1, 0);

@@ -49,6 +49,7 @@ cudaError_t NR_INST_NAME(int allt, int esm, int zs, const void* dg, const void* 
     if (allt == 2 && zs == 384) return launch_one(nr_decode_kernel<float, true, BG, 2, 0, 384>, dg, da, grid, nT, smem, s);
     if (allt == 2 && zs == 0) return launch_one(nr_decode_kernel<float, true, BG, 2, 0, 0>, dg, da, grid, nT, smem, s);
     if (allt == 1 && zs == 0) return launch_one(nr_decode_kernel<float, true, BG, 1, 0, 0>, dg, da, grid, nT, smem, s);
+    if (allt == 0 && zs == 0) return launch_one(nr_decode_kernel<float, true, BG, 0, 0, 0>, dg, da, grid, nT, smem, s);   // tiered state (low rates)
 #endif
     return cudaErrorNotSupported;
 }
