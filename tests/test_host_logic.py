@@ -130,3 +130,18 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
     assert sizes == [ctypes.sizeof(_native.TbConfig), ctypes.sizeof(_native.TbGroup)]
     want = [getattr(_native.TbConfig, f).offset for f in fields_cfg] + [getattr(_native.TbGroup, f).offset for f in fields_grp]
     assert offs == want
+
+
+def test_decoder_flags_word_matches_the_header():
+    """_native.dec_flags builds the `flags` word of include/nrldpc.h: NRLDPC_DEC_EARLY_STOP | NRLDPC_DEC_ES_FROM(k), or
+    NRLDPC_DEC_ES_AUTO for earlyStopFrom='auto'; the constants are the header's."""
+    hdr = open(os.path.join(ROOT, "include", "nrldpc.h")).read()
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"(NRLDPC_DEC_[A-Z_]+) = (\d+)", hdr)}
+    assert enum == {"NRLDPC_DEC_EARLY_STOP": _native.DEC_EARLY_STOP, "NRLDPC_DEC_ALL_ROWS": _native.DEC_ALL_ROWS,
+                    "NRLDPC_DEC_ES_AUTO": _native.DEC_ES_AUTO}
+    assert _native.dec_flags(False, 5) == 0 and _native.dec_flags(False, "auto") == 0
+    assert _native.dec_flags(True) == 1 | (1 << 8)
+    assert _native.dec_flags(True, 6) == 1 | (6 << 8) and _native.dec_flags(True, 1000) == 1 | (255 << 8) and _native.dec_flags(True, -3) == 1
+    assert _native.dec_flags(True, "auto") == 1 | 4
+    with pytest.raises(ValueError):
+        _native.dec_flags(True, "sometimes")
