@@ -117,9 +117,8 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
         const size_t budget3 = min((size_t)h->smemPerSM / 3 - kCtaSmemOverhead, (size_t)h->maxSmemOptin);
         w8AllT = a.numRows <= 16;
         w8 = rBytes + miscBytes + (size_t)(w8AllT ? 0 : a.numRows - 16) * rowBytes <= budget3;
-        // low code rates: still three CTAs per SM, the rows beyond Tensor Memory and the planes in the L2 scratch ("w8 tiered")
         if (w8) occ = 3;
-        else w8Eligible = rBytes + miscBytes + 2 * rowBytes <= budget3;
+        else w8Eligible = rBytes + miscBytes + 2 * rowBytes <= budget3;   // candidates of the "w8 tiered" route below
     }
     bool split = w8 && !w8AllT;
     if (!w8 && staticRows && h->decOcc <= 0 && occ == 2 && !h->noTmem && a.numRows > 21 && !getenv("NRLDPC_NO_SPLIT")) {
@@ -128,6 +127,8 @@ int launch_decode(nrldpc_handle* h, const NrGraph& g, DecArgs& a, cudaStream_t s
     }
     // low code rates on narrow CTAs: when the rows fit neither the three-CTA planes nor the two-CTA split, keep THREE CTAs per SM with
     // the rows beyond Tensor Memory and the planes in the L2 scratch ("w8 tiered") instead of two tiered CTAs / one all-TMEM CTA
+    // (measured at 8 waves, G edge-updates/s: all 46 rows of BG1 Zc=256 572 -> 747, Zc=224 501 -> 689; 42 rows Zc=256 668 -> 752,
+    // Zc=240 574 -> 674, Zc=208 507 -> 623; BG2 all rows Zc=240 513 -> 626.  Where the split fits it stays: 1016 vs 783 at 36 rows)
     if (w8Eligible && !split) {
         const char* wt = getenv("NRLDPC_W8_TIERED_FROM");
         const bool wouldBeOne = a.numRows * 3 * 4 > 256 && a.numRows * 3 * 4 <= 512;
